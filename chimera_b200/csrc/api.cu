@@ -1,0 +1,522 @@
+// api.cu -- C ABI of libchimera_b200.so (see include/chimera_b200.h).
+// Host-side runtime: device memory ownership, one-time uploads, pixel bucketing of the
+// posterior samples, kernel sequencing on the handle's stream, and the host epilogue.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <unordered_map>
+#include <vector>
+#include "common.cuh"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaError_t alloc(size_t count) {
+    if (count <= n && p) return cudaSuccess;
+    release();
+    cudaError_t e = cudaMalloc((void**)&p, std::max<size_t>(count, 1) * sizeof(T));
+    if (e == cudaSuccess) n = count; else p = nullptr;
+    return e;
+  }
+  cudaError_t upload(const T* src, size_t count) {
+    cudaError_t e = alloc(count);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(p, src, count * sizeof(T), cudaMemcpyHostToDevice);
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+}  // namespace
+
+struct chb_handle {
+  chb_config cfg;
+  ModelCfg mc;
+  std::string err;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  int sm_count = 148;
+  int max_smem_optin = 0;
+  int64_t launches = 0;
+  double timings[4] = {0, 0, 0, 0};
+
+  // events
+  int64_t Nev = 0, Ns = 0, Nz = 0, P = 0, Ninj = 0;
+  bool have_events = false, have_pixels = false, have_catalog = false, have_inj = false, dirty = true;
+  std::vector<double> h_m1, h_m2, h_dL, h_prior, h_ra, h_dec;      // host copies until prepare()
+  std::vector<int64_t> h_pixels, h_pe_pix;
+  std::vector<double> h_ra_pix;
+  DevBuf<double> m1d, m2d, dL, prior, ra, dec, zgrids, ra_pix, dec_pix, gw_pdf, p_cat, P_compl;
+  DevBuf<int> pix_off, neff_pix;
+  DevBuf<double> inj_m1, inj_m2, inj_dL, inj_pd;
+  // per-eval buffers
+  DevBuf<double> hyper, tabs, HC, log_like, like_raw, tile_part, partials, pgw, scratch;
+  int64_t last_n_hyper = 0;
+  int num_grid = 0;
+  size_t num_smem = 0;
+  bool stage_in_smem = true;
+};
+
+static int fail(chb_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg; else g_create_error = msg;
+  return code;
+}
+static int cuda_fail(chb_handle* h, cudaError_t e, const char* what) {
+  return fail(h, CHB_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(call, what) do { cudaError_t _e = (call); if (_e != cudaSuccess) return cuda_fail(h, _e, what); } while (0)
+
+static int validate_cfg(const chb_config* c, std::string& why) {
+  if (!c) { why = "cfg is NULL"; return CHB_ERR_INVALID; }
+  if (c->abi_version != CHB_ABI_VERSION) { why = "abi_version mismatch"; return CHB_ERR_INVALID; }
+  if (c->cosmo_model < 0 || c->cosmo_model > CHB_COSMO_MG_FLRW) { why = "unknown cosmo_model"; return CHB_ERR_INVALID; }
+  if (c->mass_model < 0 || c->mass_model > CHB_MASS_PLP) { why = "unknown mass_model"; return CHB_ERR_INVALID; }
+  if (c->rate_model < 0 || c->rate_model > CHB_RATE_TRUNC_PL) { why = "unknown rate_model"; return CHB_ERR_INVALID; }
+  if (c->cosmo_grid_res < 4 || c->mass_grid_res < 4) { why = "table resolution too small"; return CHB_ERR_INVALID; }
+  if (c->kind_p_gw < CHB_PGW_1D || c->kind_p_gw > CHB_PGW_FULL) {
+    why = "`kind_p_gw3d` must be one of `approximate`, `marginalized`, or `full`"; return CHB_ERR_INVALID; }
+  if (c->kernel != CHB_KERNEL_EPAN && c->kernel != CHB_KERNEL_GAUSS) { why = "unknown kernel"; return CHB_ERR_INVALID; }
+  if (c->bw_method < CHB_BW_SCOTT || c->bw_method > CHB_BW_SCALAR) {
+    why = "bw_method should be 'scott', 'silverman', or a scalar"; return CHB_ERR_INVALID; }
+  if (c->binning && c->num_bins < 1) { why = "num_bins must be positive"; return CHB_ERR_INVALID; }
+  if (c->kind_p_gw == CHB_PGW_FULL && !c->use_cut_grid) {
+    why = "kind_p_gw3d='full' needs a numeric cut_grid"; return CHB_ERR_UNSUPPORTED; }
+  if (c->fp_mode != CHB_FP64 && c->fp_mode != CHB_FP32) { why = "unknown fp_mode"; return CHB_ERR_INVALID; }
+  return CHB_OK;
+}
+
+static ModelCfg model_cfg(const chb_config& c) {
+  ModelCfg m;
+  m.cosmo_model = c.cosmo_model; m.mass_model = c.mass_model; m.rate_model = c.rate_model;
+  m.catalog_kind = c.catalog_kind; m.compl_z_lo = c.compl_z_lo; m.compl_z_hi = c.compl_z_hi;
+  m.lay = make_layout(c.cosmo_grid_res, c.mass_grid_res);
+  return m;
+}
+
+extern "C" {
+
+int chb_abi_version(void) { return CHB_ABI_VERSION; }
+
+int chb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+const char* chb_last_error(const chb_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int chb_create(chb_handle** out, const chb_config* cfg) {
+  if (!out) return fail(nullptr, CHB_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  std::string why;
+  int rc = validate_cfg(cfg, why);
+  if (rc != CHB_OK) return fail(nullptr, rc, why);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(nullptr, CHB_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, CHB_ERR_INVALID, "device ordinal out of range");
+  if ((e = cudaSetDevice(cfg->device)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaSetDevice");
+  chb_handle* h = new chb_handle();
+  h->cfg = *cfg;
+  h->mc = model_cfg(*cfg);
+  cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, cfg->device);
+  cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
+  if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    delete h; return cuda_fail(nullptr, e, "cudaStreamCreate"); }
+  for (auto& evn : h->ev) cudaEventCreate(&evn);
+  *out = h;
+  return CHB_OK;
+}
+
+void chb_destroy(chb_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  DevBuf<double>* dbl[] = {&h->m1d, &h->m2d, &h->dL, &h->prior, &h->ra, &h->dec, &h->zgrids, &h->ra_pix, &h->dec_pix,
+                           &h->gw_pdf, &h->p_cat, &h->P_compl, &h->inj_m1, &h->inj_m2, &h->inj_dL, &h->inj_pd,
+                           &h->hyper, &h->tabs, &h->HC, &h->log_like, &h->like_raw, &h->tile_part, &h->partials, &h->pgw, &h->scratch};
+  for (auto* b : dbl) b->release();
+  h->pix_off.release();
+  h->neff_pix.release();
+  for (auto& evn : h->ev) if (evn) cudaEventDestroy(evn);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int chb_set_events(chb_handle* h, int64_t Nev, int64_t Ns, int64_t Nz, const double* m1det, const double* m2det,
+                   const double* dL, const double* pe_prior, const double* ra, const double* dec,
+                   const double* z_grids) {
+  if (!h) return CHB_ERR_INVALID;
+  if (Nev < 1 || Ns < 1 || Nz < 2) return fail(h, CHB_ERR_INVALID, "need Nev>=1, Ns>=1, Nz>=2");
+  if (Ns > (1 << 30) / 4 || Nev * Ns > (int64_t)1 << 40) return fail(h, CHB_ERR_INVALID, "event arrays too large");
+  if (!m1det || !m2det || !dL || !pe_prior || !z_grids) return fail(h, CHB_ERR_INVALID, "NULL event array");
+  if (h->cfg.kind_p_gw == CHB_PGW_FULL && (!ra || !dec)) return fail(h, CHB_ERR_INVALID, "kind 'full' needs ra/dec samples");
+  if (h->cfg.use_cut_grid && Nz / 2 < 2) return fail(h, CHB_ERR_INVALID, "z_int_res//2 must be >= 2");
+  cudaSetDevice(h->cfg.device);
+  const size_t n = (size_t)Nev * Ns;
+  h->Nev = Nev; h->Ns = Ns; h->Nz = Nz;
+  h->h_m1.assign(m1det, m1det + n); h->h_m2.assign(m2det, m2det + n);
+  h->h_dL.assign(dL, dL + n); h->h_prior.assign(pe_prior, pe_prior + n);
+  if (ra && dec) { h->h_ra.assign(ra, ra + n); h->h_dec.assign(dec, dec + n); } else { h->h_ra.clear(); h->h_dec.clear(); }
+  CU(h->zgrids.upload(z_grids, (size_t)Nev * Nz), "upload z_grids");
+  h->have_events = true; h->have_pixels = false; h->have_catalog = false; h->dirty = true;
+  return CHB_OK;
+}
+
+int chb_set_pixels(chb_handle* h, int64_t P, const int64_t* pixels_opt_nsides, const int64_t* pixels_pe_opt_nside,
+                   const double* ra_pix, const double* dec_pix, const double* gw_loc2d_pdf) {
+  if (!h) return CHB_ERR_INVALID;
+  if (!h->have_events) return fail(h, CHB_ERR_STATE, "chb_set_events must come first");
+  if (P < 1 || !pixels_opt_nsides || !ra_pix || !dec_pix || !gw_loc2d_pdf)
+    return fail(h, CHB_ERR_INVALID, "NULL pixel array or P < 1");
+  if (h->cfg.kind_p_gw == CHB_PGW_MARG && !pixels_pe_opt_nside)
+    return fail(h, CHB_ERR_INVALID, "kind 'marginalized' needs pixels_pe_opt_nside");
+  cudaSetDevice(h->cfg.device);
+  h->P = P;
+  const size_t np = (size_t)h->Nev * P;
+  h->h_pixels.assign(pixels_opt_nsides, pixels_opt_nsides + np);
+  if (pixels_pe_opt_nside) h->h_pe_pix.assign(pixels_pe_opt_nside, pixels_pe_opt_nside + (size_t)h->Nev * h->Ns);
+  else h->h_pe_pix.clear();
+  h->h_ra_pix.assign(ra_pix, ra_pix + np);
+  CU(h->ra_pix.upload(ra_pix, np), "upload ra_pix");
+  CU(h->dec_pix.upload(dec_pix, np), "upload dec_pix");
+  CU(h->gw_pdf.upload(gw_loc2d_pdf, np), "upload gw_loc2d_pdf");
+  // neff_pixels = count(ra_pix != -100)  (catalog.py:121)
+  std::vector<int> neff(h->Nev);
+  for (int64_t e = 0; e < h->Nev; ++e) {
+    int c = 0;
+    for (int64_t p = 0; p < P; ++p) c += (ra_pix[e * P + p] != -100.0);
+    neff[e] = c;
+  }
+  CU(h->neff_pix.upload(neff.data(), neff.size()), "upload neff_pixels");
+  h->have_pixels = true; h->dirty = true;
+  return CHB_OK;
+}
+
+int chb_set_catalog(chb_handle* h, const double* p_cat, const double* P_compl) {
+  if (!h) return CHB_ERR_INVALID;
+  if (!h->have_pixels) return fail(h, CHB_ERR_STATE, "chb_set_pixels must come first");
+  if (!p_cat || !P_compl) return fail(h, CHB_ERR_INVALID, "NULL catalogue array");
+  if (h->cfg.catalog_kind != 1) return fail(h, CHB_ERR_INVALID, "config has catalog_kind=0 (empty catalogue)");
+  cudaSetDevice(h->cfg.device);
+  CU(h->p_cat.upload(p_cat, (size_t)h->Nev * h->P * h->Nz), "upload p_cat");
+  CU(h->P_compl.upload(P_compl, (size_t)h->Nev * h->Nz), "upload P_compl");
+  h->have_catalog = true;
+  return CHB_OK;
+}
+
+int chb_set_injections(chb_handle* h, int64_t Ninj, const double* m1det, const double* m2det, const double* dL,
+                       const double* p_draw) {
+  if (!h) return CHB_ERR_INVALID;
+  if (Ninj < 1 || Ninj > 0x7fffffff || !m1det || !m2det || !dL || !p_draw)
+    return fail(h, CHB_ERR_INVALID, "bad injection arrays");
+  cudaSetDevice(h->cfg.device);
+  CU(h->inj_m1.upload(m1det, Ninj), "upload inj m1det");
+  CU(h->inj_m2.upload(m2det, Ninj), "upload inj m2det");
+  CU(h->inj_dL.upload(dL, Ninj), "upload inj dL");
+  CU(h->inj_pd.upload(p_draw, Ninj), "upload inj p_draw");
+  h->Ninj = Ninj; h->have_inj = true;
+  return CHB_OK;
+}
+
+// One-time device layout of the event samples.  For the marginalised KDE the samples of every
+// event are bucketed by pixel slot (slot i <-> pixels_opt_nsides[ev][i]; unmatched -> slot P),
+// so that `pe_pix == pixels[i]` (likelihood.py:176) becomes a contiguous range.  All per-event
+// reductions are order-independent, so the other variants use the same permuted arrays.
+static int prepare(chb_handle* h) {
+  if (!h->dirty) return CHB_OK;
+  const int64_t Nev = h->Nev, Ns = h->Ns, P = h->P;
+  const size_t n = (size_t)Nev * Ns;
+  const bool bucket = h->have_pixels && !h->h_pe_pix.empty();
+  if (bucket) {
+    std::vector<int> off((size_t)Nev * (P + 2));
+    std::vector<double> t1(n), t2(n), t3(n), t4(n), t5, t6;
+    const bool sky = !h->h_ra.empty();
+    if (sky) { t5.resize(n); t6.resize(n); }
+    std::vector<int> slot(Ns), cnt(P + 2);
+    for (int64_t e = 0; e < Nev; ++e) {
+      std::unordered_map<int64_t, int> map;
+      for (int64_t p = 0; p < P; ++p) {
+        int64_t pid = h->h_pixels[e * P + p];
+        if (pid != -100 && !map.count(pid)) map[pid] = (int)p;
+      }
+      std::fill(cnt.begin(), cnt.end(), 0);
+      for (int64_t j = 0; j < Ns; ++j) {
+        auto it = map.find(h->h_pe_pix[e * Ns + j]);
+        slot[j] = (it == map.end()) ? (int)P : it->second;
+        cnt[slot[j] + 1]++;
+      }
+      for (int64_t p = 0; p <= P; ++p) cnt[p + 1] += cnt[p];
+      for (int64_t p = 0; p <= P + 1; ++p) off[e * (P + 2) + p] = cnt[p];
+      std::vector<int> cur(cnt.begin(), cnt.end() - 1);
+      for (int64_t j = 0; j < Ns; ++j) {
+        size_t d = (size_t)e * Ns + cur[slot[j]]++, s = (size_t)e * Ns + j;
+        t1[d] = h->h_m1[s]; t2[d] = h->h_m2[s]; t3[d] = h->h_dL[s]; t4[d] = h->h_prior[s];
+        if (sky) { t5[d] = h->h_ra[s]; t6[d] = h->h_dec[s]; }
+      }
+    }
+    CU(h->m1d.upload(t1.data(), n), "upload m1det"); CU(h->m2d.upload(t2.data(), n), "upload m2det");
+    CU(h->dL.upload(t3.data(), n), "upload dL"); CU(h->prior.upload(t4.data(), n), "upload pe_prior");
+    if (sky) { CU(h->ra.upload(t5.data(), n), "upload ra"); CU(h->dec.upload(t6.data(), n), "upload dec"); }
+    CU(h->pix_off.upload(off.data(), off.size()), "upload pixel offsets");
+  } else {
+    CU(h->m1d.upload(h->h_m1.data(), n), "upload m1det"); CU(h->m2d.upload(h->h_m2.data(), n), "upload m2det");
+    CU(h->dL.upload(h->h_dL.data(), n), "upload dL"); CU(h->prior.upload(h->h_prior.data(), n), "upload pe_prior");
+    if (!h->h_ra.empty()) { CU(h->ra.upload(h->h_ra.data(), n), "upload ra"); CU(h->dec.upload(h->h_dec.data(), n), "upload dec"); }
+  }
+  h->dirty = false;
+  return CHB_OK;
+}
+
+static int eval_impl(chb_handle* h, int64_t n_hyper, const double* d_hyper, double* d_log_like, double* d_partials,
+                     double* d_pgw, cudaStream_t s) {
+  const chb_config& c = h->cfg;
+  const bool do_num = h->have_events, do_sel = h->have_inj;
+  if (do_num) {
+    if (c.kind_p_gw != CHB_PGW_1D && !h->have_pixels) return fail(h, CHB_ERR_STATE, "pixelated kind needs chb_set_pixels");
+    if (c.catalog_kind == 1 && c.kind_p_gw != CHB_PGW_1D && !h->have_catalog)
+      return fail(h, CHB_ERR_STATE, "catalog_kind=1 needs chb_set_catalog");
+    int rc = prepare(h);
+    if (rc != CHB_OK) return rc;
+  }
+  const TableLayout lay = h->mc.lay;
+  CU(h->tabs.alloc((size_t)n_hyper * lay.total()), "alloc tables");
+  CU(h->HC.alloc((size_t)n_hyper * CHB_NHC), "alloc constants");
+  cudaEventRecord(h->ev[0], s);
+  CU(launch_build_tables(h->mc, (int)n_hyper, d_hyper, h->tabs.p, h->HC.p, s), "build_tables launch");
+  h->launches++;
+  cudaEventRecord(h->ev[1], s);
+
+  double* ll = nullptr;
+  if (do_num) {
+    ll = d_log_like;
+    if (!ll) { CU(h->log_like.alloc((size_t)n_hyper * h->Nev), "alloc log_like"); ll = h->log_like.p; }
+    NumArgs a;
+    memset(&a, 0, sizeof(a));
+    a.mc = h->mc;
+    a.kind = c.kind_p_gw; a.kernel = c.kernel; a.bw_method = c.bw_method; a.use_cut = c.use_cut_grid;
+    a.binning = (c.kind_p_gw == CHB_PGW_FULL) ? 0 : c.binning; a.num_bins = c.num_bins; a.fp_mode = c.fp_mode;
+    a.bw_value = c.bw_value; a.cut_grid = c.cut_grid; a.pe_neff = c.pe_neff;
+    a.Nev = (int)h->Nev; a.Ns = (int)h->Ns; a.Nz = (int)h->Nz; a.P = (int)std::max<int64_t>(h->P, 1);
+    a.m1d = h->m1d.p; a.m2d = h->m2d.p; a.dL = h->dL.p; a.prior = h->prior.p; a.ra = h->ra.p; a.dec = h->dec.p;
+    a.zgrids = h->zgrids.p; a.pix_off = h->pix_off.p; a.ra_pix = h->ra_pix.p; a.dec_pix = h->dec_pix.p;
+    a.gw_pdf = h->gw_pdf.p; a.neff_pix = h->neff_pix.p;
+    a.p_cat = h->have_catalog ? h->p_cat.p : nullptr; a.P_compl = h->have_catalog ? h->P_compl.p : nullptr;
+    if (!h->have_catalog) a.mc.catalog_kind = 0;
+    a.n_hyper = (int)n_hyper; a.hyper = d_hyper; a.tabs = h->tabs.p; a.HC = h->HC.p;
+    CU(h->like_raw.alloc((size_t)n_hyper * h->Nev), "alloc like_raw");
+    a.log_like = ll; a.like_raw = h->like_raw.p; a.p_gw_out = d_pgw;
+    h->last_n_hyper = n_hyper;
+    if (c.kind_p_gw == CHB_PGW_MARG && !h->pix_off.p) return fail(h, CHB_ERR_STATE, "marginalized kind needs pixels_pe_opt_nside");
+    // sample staging in shared memory when it fits, else per-CTA global scratch (L2-resident)
+    size_t smem = numerator_smem_bytes(a, true);
+    h->stage_in_smem = smem <= (size_t)h->max_smem_optin;
+    if (!h->stage_in_smem) smem = numerator_smem_bytes(a, false);
+    if (smem > (size_t)h->max_smem_optin) return fail(h, CHB_ERR_UNSUPPORTED, "z grid / tables do not fit in shared memory");
+    CU(numerator_configure(smem), "numerator smem opt-in");
+    const long long units = (long long)h->Nev * n_hyper;
+    int grid = (int)std::min<long long>(units, (long long)h->sm_count);
+    if (!h->stage_in_smem) {
+      a.scratch_stride = numerator_scratch_doubles(a);
+      CU(h->scratch.alloc((size_t)grid * a.scratch_stride), "alloc staging scratch");
+      a.scratch = h->scratch.p;
+    }
+    h->num_grid = grid; h->num_smem = smem;
+    CU(launch_numerator(a, grid, numerator_block_threads(), smem, s), "numerator launch");
+    h->launches++;
+  }
+  cudaEventRecord(h->ev[2], s);
+
+  int tiles = 0;
+  if (do_sel) {
+    // enough CTAs to fill the machine even for a single hyper-point; >= 1024 injections per tile
+    long long want = (4LL * h->sm_count + n_hyper - 1) / n_hyper;
+    long long maxt = std::max<long long>(1, h->Ninj / 1024);
+    tiles = (int)std::max<long long>(1, std::min(want, maxt));
+    CU(h->tile_part.alloc((size_t)n_hyper * tiles * 2), "alloc selection partials");
+    SelArgs sa;
+    sa.mc = h->mc; sa.Ninj = (int)h->Ninj; sa.n_hyper = (int)n_hyper; sa.tiles = tiles;
+    sa.m1d = h->inj_m1.p; sa.m2d = h->inj_m2.p; sa.dL = h->inj_dL.p; sa.p_draw = h->inj_pd.p;
+    sa.hyper = d_hyper; sa.tabs = h->tabs.p; sa.HC = h->HC.p; sa.tile_part = h->tile_part.p;
+    CU(launch_selection(sa, s), "selection launch");
+    h->launches++;
+  }
+  cudaEventRecord(h->ev[3], s);
+  CU(launch_reduce((int)n_hyper, (int)h->Nev, tiles, do_num ? ll : nullptr, do_sel ? h->tile_part.p : nullptr,
+                   d_partials, s), "reduce launch");
+  h->launches++;
+  cudaEventRecord(h->ev[4], s);
+  return CHB_OK;
+}
+
+int chb_eval_device(chb_handle* h, int64_t n_hyper, const double* d_hyper, double* d_log_like, double* d_partials,
+                    double* d_p_gw, void* cuda_stream) {
+  if (!h) return CHB_ERR_INVALID;
+  if (n_hyper < 1 || !d_hyper || !d_partials) return fail(h, CHB_ERR_INVALID, "bad eval arguments");
+  if (!h->have_events && !h->have_inj) return fail(h, CHB_ERR_STATE, "nothing to evaluate: set events and/or injections");
+  cudaSetDevice(h->cfg.device);
+  cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+  return eval_impl(h, n_hyper, d_hyper, d_log_like, d_partials, d_p_gw, s);
+}
+
+int chb_eval(chb_handle* h, int64_t n_hyper, const double* hyper, double* log_like_evs, double* partials, double* p_gw) {
+  if (!h) return CHB_ERR_INVALID;
+  if (n_hyper < 1 || !hyper || !partials) return fail(h, CHB_ERR_INVALID, "bad eval arguments");
+  if (!h->have_events && !h->have_inj) return fail(h, CHB_ERR_STATE, "nothing to evaluate: set events and/or injections");
+  cudaSetDevice(h->cfg.device);
+  cudaStream_t s = h->stream;
+  CU(h->hyper.alloc((size_t)n_hyper * CHB_NPAR), "alloc hyper");
+  CU(h->partials.alloc((size_t)n_hyper * 3), "alloc partials");
+  CU(cudaMemcpyAsync(h->hyper.p, hyper, (size_t)n_hyper * CHB_NPAR * sizeof(double), cudaMemcpyHostToDevice, s), "H2D hyper");
+  double* d_ll = nullptr;
+  double* d_pgw = nullptr;
+  size_t pgw_n = 0;
+  if (h->have_events) {
+    CU(h->log_like.alloc((size_t)n_hyper * h->Nev), "alloc log_like");
+    d_ll = h->log_like.p;
+    if (p_gw) {
+      pgw_n = (size_t)n_hyper * h->Nev * (h->cfg.kind_p_gw == CHB_PGW_1D ? 1 : h->P) * h->Nz;
+      CU(h->pgw.alloc(pgw_n), "alloc p_gw");
+      d_pgw = h->pgw.p;
+    }
+  }
+  int rc = eval_impl(h, n_hyper, h->hyper.p, d_ll, h->partials.p, d_pgw, s);
+  if (rc != CHB_OK) return rc;
+  if (log_like_evs && d_ll)
+    CU(cudaMemcpyAsync(log_like_evs, d_ll, (size_t)n_hyper * h->Nev * sizeof(double), cudaMemcpyDeviceToHost, s), "D2H log_like");
+  CU(cudaMemcpyAsync(partials, h->partials.p, (size_t)n_hyper * 3 * sizeof(double), cudaMemcpyDeviceToHost, s), "D2H partials");
+  if (d_pgw) CU(cudaMemcpyAsync(p_gw, d_pgw, pgw_n * sizeof(double), cudaMemcpyDeviceToHost, s), "D2H p_gw");
+  CU(cudaStreamSynchronize(s), "eval synchronize");
+  for (int i = 0; i < 4; ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]);
+    h->timings[i] = ms;
+  }
+  return CHB_OK;
+}
+
+int chb_last_numlike_evs(chb_handle* h, double* like_evs) {
+  if (!h || !like_evs) return CHB_ERR_INVALID;
+  if (!h->have_events || h->last_n_hyper < 1 || !h->like_raw.p) return fail(h, CHB_ERR_STATE, "no numerator evaluated yet");
+  cudaSetDevice(h->cfg.device);
+  CU(cudaStreamSynchronize(h->stream), "synchronize");
+  CU(cudaMemcpy(like_evs, h->like_raw.p, (size_t)h->last_n_hyper * h->Nev * sizeof(double), cudaMemcpyDeviceToHost), "D2H like");
+  return CHB_OK;
+}
+
+int chb_finalize(const chb_config* cfg, int64_t n_hyper, int64_t Nev_total, const double* hyper, const double* partials,
+                 double* log_like_num, double* log_Nexp, double* log_hyper, double* neff_inj, double* N_exp) {
+  if (!cfg || n_hyper < 1 || !hyper || !partials) return CHB_ERR_INVALID;
+  const double Ninj = cfg->N_inj;
+  for (int64_t i = 0; i < n_hyper; ++i) {
+    const double R0 = hyper[i * CHB_NPAR + CHB_P_R0];
+    double lnum = partials[i * 3 + 0];
+    const double s1 = partials[i * 3 + 1], s2 = partials[i * 3 + 2];
+    const double xi = s1 / Ninj;                                      // selection_function.py:39
+    double Nexp = cfg->Tobs * xi;                                     // :41
+    double neff = std::numeric_limits<double>::quiet_NaN();
+    if (cfg->check_neff) {
+      const double var = s2 / (Ninj * Ninj) - xi * xi / Ninj;         // :44
+      neff = xi * xi / var;                                           // :45
+      if (neff < cfg->N_eff) Nexp = 0.0;                              // :46-47
+    }
+    double lh;
+    if (!cfg->scale_free) {                                           // likelihood.py:299-300,313-316
+      lnum += (double)Nev_total * std::log(R0 * cfg->Tobs);
+      lh = lnum - Nexp;
+    } else {
+      lh = lnum - (double)Nev_total * std::log(Nexp);
+    }
+    if (log_like_num) log_like_num[i] = lnum;
+    if (log_Nexp) log_Nexp[i] = std::log(Nexp);
+    if (log_hyper) log_hyper[i] = lh;
+    if (neff_inj) neff_inj[i] = neff;
+    if (N_exp) N_exp[i] = Nexp;
+  }
+  return CHB_OK;
+}
+
+static int model_tables_device(const chb_config* cfg, const double* params, ModelCfg& mc, DevBuf<double>& dP,
+                               DevBuf<double>& dT, DevBuf<double>& dHC) {
+  chb_handle* h = nullptr;
+  std::string why;
+  int rc = validate_cfg(cfg, why);
+  if (rc != CHB_OK) return fail(nullptr, rc, why);
+  if (!params) return fail(nullptr, CHB_ERR_INVALID, "params is NULL");
+  if (chb_device_count() == 0) return fail(nullptr, CHB_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  CU(cudaSetDevice(cfg->device), "cudaSetDevice");
+  mc = model_cfg(*cfg);
+  CU(dP.upload(params, CHB_NPAR), "upload params");
+  CU(dT.alloc(mc.lay.total()), "alloc tables");
+  CU(dHC.alloc(CHB_NHC), "alloc constants");
+  CU(launch_build_tables(mc, 1, dP.p, dT.p, dHC.p, 0), "build_tables launch");
+  return CHB_OK;
+}
+
+int chb_model_eval(const chb_config* cfg, int which, const double* params, int64_t n, const double* a, const double* b,
+                   const double* c, double* out) {
+  chb_handle* h = nullptr;
+  if (n < 0 || (n > 0 && (!a || !out))) return fail(nullptr, CHB_ERR_INVALID, "bad array arguments");
+  if ((which == CHB_F_P_M1M2 && !b) || (which == CHB_F_POP_RATE_DET_INJ && (!b || !c)))
+    return fail(nullptr, CHB_ERR_INVALID, "missing array argument");
+  ModelCfg mc;
+  DevBuf<double> dP, dT, dHC, da, db, dc, dout;
+  int rc = model_tables_device(cfg, params, mc, dP, dT, dHC);
+  if (rc == CHB_OK && n > 0) {
+    do {
+      cudaError_t e;
+      if ((e = da.upload(a, n)) != cudaSuccess) { rc = cuda_fail(nullptr, e, "upload a"); break; }
+      if (b && (e = db.upload(b, n)) != cudaSuccess) { rc = cuda_fail(nullptr, e, "upload b"); break; }
+      if (c && (e = dc.upload(c, n)) != cudaSuccess) { rc = cuda_fail(nullptr, e, "upload c"); break; }
+      if ((e = dout.alloc(n)) != cudaSuccess) { rc = cuda_fail(nullptr, e, "alloc out"); break; }
+      if ((e = launch_model_eval(mc, which, dP.p, dT.p, dHC.p, n, da.p, b ? db.p : nullptr, c ? dc.p : nullptr, dout.p, 0)) != cudaSuccess) {
+        rc = cuda_fail(nullptr, e, "model_eval launch"); break; }
+      if ((e = cudaMemcpy(out, dout.p, n * sizeof(double), cudaMemcpyDeviceToHost)) != cudaSuccess) {
+        rc = cuda_fail(nullptr, e, "D2H out"); break; }
+    } while (0);
+  }
+  dP.release(); dT.release(); dHC.release(); da.release(); db.release(); dc.release(); dout.release();
+  (void)h;
+  return rc;
+}
+
+int chb_model_tables(const chb_config* cfg, const double* params, double* z_grid_interp, double* integral_invE_interp,
+                     double* m_grid, double* cdf_m2_conditioned, double* norm_p_m1) {
+  ModelCfg mc;
+  DevBuf<double> dP, dT, dHC;
+  int rc = model_tables_device(cfg, params, mc, dP, dT, dHC);
+  if (rc == CHB_OK) {
+    std::vector<double> T(mc.lay.total()), HC(CHB_NHC);
+    cudaError_t e = cudaMemcpy(T.data(), dT.p, T.size() * sizeof(double), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(HC.data(), dHC.p, HC.size() * sizeof(double), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = cuda_fail(nullptr, e, "D2H tables");
+    else {
+      if (z_grid_interp) memcpy(z_grid_interp, T.data() + mc.lay.off_zg(), mc.lay.rc * sizeof(double));
+      if (integral_invE_interp) memcpy(integral_invE_interp, T.data() + mc.lay.off_iinv(), mc.lay.rc * sizeof(double));
+      if (m_grid) memcpy(m_grid, T.data() + mc.lay.off_mg(), mc.lay.rm * sizeof(double));
+      if (cdf_m2_conditioned) memcpy(cdf_m2_conditioned, T.data() + mc.lay.off_cdf(), mc.lay.rm * sizeof(double));
+      if (norm_p_m1) *norm_p_m1 = HC[HC_NORM_P_M1];
+    }
+  }
+  dP.release(); dT.release(); dHC.release();
+  return rc;
+}
+
+int64_t chb_kernel_launch_count(const chb_handle* h) { return h ? h->launches : 0; }
+
+int chb_last_timings(const chb_handle* h, double out[4]) {
+  if (!h || !out) return CHB_ERR_INVALID;
+  for (int i = 0; i < 4; ++i) out[i] = h->timings[i];
+  return CHB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,62 @@
+// common.cuh -- argument blocks and launcher prototypes shared by the kernels and the C ABI.
+#pragma once
+#include "models.cuh"
+
+struct ModelCfg {
+  int cosmo_model, mass_model, rate_model;
+  int catalog_kind;
+  double compl_z_lo, compl_z_hi;
+  TableLayout lay;
+};
+
+// Everything the fused numerator kernel needs (device pointers).
+struct NumArgs {
+  ModelCfg mc;
+  // hyperlikelihood options (likelihood.py:48-62)
+  int kind, kernel, bw_method, use_cut, binning, num_bins, fp_mode;
+  double bw_value, cut_grid, pe_neff;
+  // event data, samples permuted so that each pixel's samples are contiguous
+  int Nev, Ns, Nz, P;
+  const double *m1d, *m2d, *dL, *prior, *ra, *dec;   // (Nev, Ns)
+  const double* zgrids;                              // (Nev, Nz)
+  const int* pix_off;                                // (Nev, P+2) sample offsets per pixel slot
+  const double *ra_pix, *dec_pix, *gw_pdf;           // (Nev, P)
+  const int* neff_pix;                               // (Nev,)
+  const double* p_cat;                               // (Nev, P, Nz)
+  const double* P_compl;                             // (Nev, Nz)
+  // hyper-points
+  int n_hyper;
+  const double* hyper;   // (n_hyper, CHB_NPAR)
+  const double* tabs;    // (n_hyper, lay.total())
+  const double* HC;      // (n_hyper, CHB_NHC)
+  // outputs
+  double* log_like;      // (n_hyper, Nev)
+  double* like_raw;      // (n_hyper, Nev) integral before log / nan_to_num
+  double* p_gw_out;      // optional (n_hyper, Nev, [P,] Nz)
+  // per-CTA global scratch for sample staging when it does not fit in shared memory
+  double* scratch;
+  long long scratch_stride;   // doubles per CTA (0: staging lives in shared memory)
+};
+
+struct SelArgs {
+  ModelCfg mc;
+  int Ninj, n_hyper, tiles;
+  const double *m1d, *m2d, *dL, *p_draw;
+  const double *hyper, *tabs, *HC;
+  double* tile_part;     // (n_hyper, tiles, 2): nansum(w), sum(w^2) per tile
+};
+
+// launchers (each returns the cudaError_t of the launch)
+cudaError_t launch_build_tables(const ModelCfg& mc, int n_hyper, const double* d_hyper, double* d_tabs,
+                                double* d_HC, cudaStream_t s);
+cudaError_t launch_selection(const SelArgs& a, cudaStream_t s);
+cudaError_t launch_numerator(const NumArgs& a, int grid, int block, size_t smem, cudaStream_t s);
+size_t numerator_smem_bytes(const NumArgs& a, bool stage_in_smem);
+long long numerator_scratch_doubles(const NumArgs& a);
+int numerator_block_threads();
+cudaError_t numerator_configure(size_t smem);
+cudaError_t launch_reduce(int n_hyper, int Nev, int tiles, const double* d_log_like, const double* d_tile_part,
+                          double* d_partials, cudaStream_t s);
+cudaError_t launch_model_eval(const ModelCfg& mc, int which, const double* d_params, const double* d_tabs,
+                              const double* d_HC, long long n, const double* a, const double* b, const double* c,
+                              double* out, cudaStream_t s);

@@ -1,0 +1,490 @@
+// numerator.cu -- fused per-(event, hyper-point) likelihood numerator (kernels 2-4 of DESIGN.md).
+//
+// One CTA evaluates one unit = log \int K_gw,i(z,Omega|lambda) p_gal(z,Omega|lambda) psi(z)/(1+z) dz dOmega
+// for event i and hyper-point lambda, entirely on chip:
+//   stage 1  population reweighting of the event's posterior samples
+//            (pop_wrapper.py:67-80: z_from_dGW + p_m1m2 / pe_prior)              -> z_j, w_j in smem
+//   stage 2  per-event KDE of the reweighted samples on the effective z grid
+//            (likelihood.py:105-260, utils/math.py:32-89,154-229), four variants:
+//            1-D, 'approximate', 'marginalized' (per pixel), 'full' (3-D whitened Gaussian)
+//   stage 3  z-integral against p_gal * psi/(1+z) / (ddL/dz (1+z)^2), pixel sum, log,
+//            nan_to_num  (likelihood.py:266-301, pop_wrapper.py:82-90, catalog.py:197-203)
+// p_gw never touches HBM unless the caller asks for it (debug output).  The hyper-point's
+// tables arrive with one TMA bulk copy.  Grid is persistent (CTAs stride over units, hyper-point
+// fastest so that CTAs running concurrently share the same event's samples in L2).
+//
+// This file holds the fp64 reference-faithful path plus the fp32 pair-sum inner loops
+// (CHB_FP32): samples are centred and pre-scaled per unit in fp64, the G x N pair sum runs in
+// fp32 with one MUFU.EX2 per pair (Gaussian) or 3 FP32 ops (Epanechnikov), grid points held in
+// registers, samples broadcast from shared memory, warp-shuffle + fp64 cross-warp reduction.
+#include "common.cuh"
+#include "stage.cuh"
+
+#define NUM_THREADS 512
+#define NUM_WARPS (NUM_THREADS / 32)
+
+int numerator_block_threads() { return NUM_THREADS; }
+
+// shared-memory plan (offsets in doubles), identical on host and device
+struct SmemPlan {
+  int tab, zgrid, tw, dV, rj, jac, pgw, eg, dens, bc, bs, red, stage, total;
+};
+__host__ __device__ inline SmemPlan make_plan(int tab_total, int Nz, int B, int Ns, int kind, bool stage_in_smem) {
+  SmemPlan p;
+  int o = 0;
+  p.tab = o; o += tab_total;
+  p.zgrid = o; o += Nz;
+  p.tw = o; o += Nz;
+  p.dV = o; o += Nz;
+  p.rj = o; o += Nz;
+  p.jac = o; o += Nz;
+  p.pgw = o; o += Nz;
+  p.eg = o; o += Nz;
+  p.dens = o; o += Nz;
+  p.bc = o; o += B;
+  p.bs = o; o += B;
+  p.red = o; o += 64;
+  o = (o + 1) & ~1;
+  p.stage = o;
+  if (stage_in_smem) o += (kind == CHB_PGW_FULL ? 4 : 2) * Ns;
+  p.total = o;
+  return p;
+}
+size_t numerator_smem_bytes(const NumArgs& a, bool stage_in_smem) {
+  return (size_t)make_plan(a.mc.lay.total(), a.Nz, a.binning ? a.num_bins : 0, a.Ns, a.kind, stage_in_smem).total * sizeof(double);
+}
+long long numerator_scratch_doubles(const NumArgs& a) {
+  return (long long)(a.kind == CHB_PGW_FULL ? 4 : 2) * a.Ns;
+}
+
+// ------------------------------------------------------------------------------------------
+// 1-D KDE pair sums.  dens[g] = scale * sum_j w_j K((eg[g]-x_j)/bw)
+// fp64: warp per grid point, lanes stride over the data set.
+__device__ __forceinline__ void kde1d_f64(const double* __restrict__ x, const double* __restrict__ w, int n,
+                                          const double* __restrict__ eg, int G, double bw, int kernel,
+                                          double scale, double* __restrict__ dens) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const double inv_bw = 1.0 / bw;
+  for (int g = warp; g < G; g += NUM_WARPS) {
+    const double gv = eg[g];
+    double acc = 0.0;
+    if (kernel == CHB_KERNEL_GAUSS) {
+      for (int j = lane; j < n; j += 32) {
+        double u = (gv - x[j]) / bw;
+        acc += w[j] * (exp(-0.5 * u * u) / 2.5066282746310002);
+      }
+    } else {
+      for (int j = lane; j < n; j += 32) {
+        double u = (gv - x[j]) / bw;
+        double kv = (fabs(u) <= 1.0) ? 0.75 * (1.0 - u * u) : 0.0;
+        acc += w[j] * kv;
+      }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) dens[g] = acc * scale;
+  }
+  (void)inv_bw;
+}
+
+// fp32 pair sums: data (x', w) as float2 in shared memory, x' = (x - c) * s pre-scaled so that the
+// Gaussian is 2^-(g'-x')^2 (s = sqrt(log2(e)/2)/bw) and the Epanechnikov support is |g'-x'|<=1
+// (s = 1/bw).  Every lane keeps R grid points in registers; all lanes read the same sample
+// (shared-memory broadcast); each warp takes a slice of the samples; partial sums are combined
+// across warps in fp64.
+template <int R>
+__device__ __forceinline__ void kde1d_f32_tile(const float2* __restrict__ xw, int n, const double* __restrict__ eg,
+                                               int G, int g_base, double c, double s, int kernel,
+                                               double* __restrict__ part /* [NUM_WARPS][G] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float gp[R], acc[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    int g = g_base + r * 32 + lane;
+    gp[r] = (g < G) ? (float)((eg[g] - c) * s) : 1e30f;
+    acc[r] = 0.f;
+  }
+  const int per = (n + NUM_WARPS - 1) / NUM_WARPS;
+  const int j0 = warp * per, j1 = min(n, j0 + per);
+  if (kernel == CHB_KERNEL_GAUSS) {
+#pragma unroll 2
+    for (int j = j0; j < j1; ++j) {
+      const float2 v = xw[j];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        float d = gp[r] - v.x;
+        acc[r] = fmaf(v.y, exp2f(-d * d), acc[r]);
+      }
+    }
+  } else {
+#pragma unroll 2
+    for (int j = j0; j < j1; ++j) {
+      const float2 v = xw[j];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        float d = gp[r] - v.x;
+        float k = fmaxf(1.f - d * d, 0.f);
+        acc[r] = fmaf(v.y, k, acc[r]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    int g = g_base + r * 32 + lane;
+    if (g < G) part[warp * G + g] = (double)acc[r];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double nan_to_num_log(double like) {
+  double l = log(like);                  // likelihood.py:296-297: jnp.nan_to_num(log, nan=-inf)
+  if (isnan(l)) return -INFINITY;        //   NaN -> -inf ; -inf -> -DBL_MAX ; +inf -> +DBL_MAX
+  if (isinf(l)) return l > 0 ? CHB_DBL_MAX : -CHB_DBL_MAX;
+  return l;
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+numerator_kernel(const NumArgs a) {
+  extern __shared__ __align__(16) double sm[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ double P[CHB_NPAR];
+  __shared__ double HC[CHB_NHC];
+  __shared__ double L[8];   // full-3D whitening: L00 L10 L11 L20 L21 L22, log_norm
+
+  const TableLayout lay = a.mc.lay;
+  const int Ns = a.Ns, Nz = a.Nz, Pp = a.P, B = a.binning ? a.num_bins : 0;
+  const bool in_smem = (a.scratch_stride == 0);
+  const SmemPlan pl = make_plan(lay.total(), Nz, B, Ns, a.kind, in_smem);
+  double* tab = sm + pl.tab;
+  double* zgrid = sm + pl.zgrid;
+  double* tw = sm + pl.tw;
+  double* dV = sm + pl.dV;
+  double* rj = sm + pl.rj;
+  double* jac = sm + pl.jac;
+  double* pgw = sm + pl.pgw;
+  double* eg = sm + pl.eg;
+  double* dens = sm + pl.dens;
+  double* bc = sm + pl.bc;
+  double* bs = sm + pl.bs;
+  double* red = sm + pl.red;
+  double* stage = in_smem ? (sm + pl.stage) : (a.scratch + (size_t)blockIdx.x * a.scratch_stride);
+  double* zs = stage;
+  double* ws = stage + Ns;
+  double* y1 = stage + 2 * Ns;   // full only
+  double* y2 = stage + 3 * Ns;
+
+  const double* zg = tab + lay.off_zg();
+  const double* iinv = tab + lay.off_iinv();
+  const double* dLt = tab + lay.off_dLt();
+  const double* mg = tab + lay.off_mg();
+  const double* cdf = tab + lay.off_cdf();
+  const int rc = lay.rc, rm = lay.rm;
+  const int cm = a.mc.cosmo_model, mm = a.mc.mass_model, rmod = a.mc.rate_model;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t tab_bytes = (uint32_t)(lay.total() * sizeof(double));
+  const bool pixelated = (a.kind != CHB_PGW_1D);
+  const bool has_cat = (a.mc.catalog_kind == 1);
+
+  if (tid == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  uint32_t phase = 0;
+
+  const long long units = (long long)a.Nev * a.n_hyper;
+  for (long long unit = blockIdx.x; unit < units; unit += gridDim.x) {
+    const int ev = (int)(unit / a.n_hyper), h = (int)(unit % a.n_hyper);
+    __syncthreads();                       // everyone is done with the previous unit's smem
+    if (tid == 0) {
+      fence_proxy_async();
+      mbar_expect_tx(&bar, tab_bytes);
+      bulk_g2s(tab, a.tabs + (size_t)h * lay.total(), tab_bytes, &bar);
+    }
+    if (tid < CHB_NPAR) P[tid] = a.hyper[(size_t)h * CHB_NPAR + tid];
+    if (tid >= 64 && tid < 64 + CHB_NHC) HC[tid - 64] = a.HC[(size_t)h * CHB_NHC + tid - 64];
+    const double* zgr = a.zgrids + (size_t)ev * Nz;
+    for (int k = tid; k < Nz; k += NUM_THREADS) zgrid[k] = zgr[k];
+    __syncthreads();
+    mbar_wait(&bar, phase);
+    phase ^= 1;
+
+    // ---- z-grid quantities: Jacobian, dVc/dz, psi/(1+z), trapezoid weights --------------
+    for (int k = tid; k < Nz; k += NUM_THREADS) {
+      const double z = zgrid[k];
+      const double dCt = dCt_from_dCr(P, HC, HC[HC_DH] * interp_clamped(z, zg, iinv, rc));
+      const double Ez = E_at_z(P, HC, z);
+      jac[k] = ddLdz_from(cm, P, HC, z, dCt, Ez) * ((1.0 + z) * (1.0 + z));   // likelihood.py:272,289
+      dV[k] = dVcdz_from(HC, dCt, Ez);
+      rj[k] = merger_rate(rmod, P, HC, z) / (1.0 + z);                        // pop_wrapper.py:85
+      const double zl = (k > 0) ? zgrid[k - 1] : z, zr = (k < Nz - 1) ? zgrid[k + 1] : z;
+      tw[k] = 0.5 * (zr - zl);                                                // trapezoid rule as a dot product
+    }
+
+    // ---- stage 1: reweighting ----------------------------------------------------------
+    const size_t so = (size_t)ev * Ns;
+    double s1 = 0.0, s2 = 0.0, sz = 0.0, zmn = INFINITY, zmx = -INFINITY;
+    for (int j = tid; j < Ns; j += NUM_THREADS) {
+      const double dL = __ldg(a.dL + so + j);
+      const double z = interp_clamped(dL, dLt, zg, rc);
+      const double opz = 1.0 + z;
+      const double m1 = __ldg(a.m1d + so + j) / opz, m2 = __ldg(a.m2d + so + j) / opz;
+      const double w = p_m1m2(mm, P, HC, mg, cdf, rm, m1, m2) / __ldg(a.prior + so + j);
+      zs[j] = z;
+      ws[j] = w;
+      s1 += w; s2 += w * w; sz += z;
+      zmn = fmin(zmn, z); zmx = fmax(zmx, z);
+    }
+    s1 = block_sum(s1, red);
+    s2 = block_sum(s2, red);
+    sz = block_sum(sz, red);
+    zmn = block_min(zmn, red);
+    zmx = block_max(zmx, red);
+    const double zmean = sz / Ns;
+    double sv = 0.0;
+    for (int j = tid; j < Ns; j += NUM_THREADS) { double d = zs[j] - zmean; sv += d * d; }
+    sv = block_sum(sv, red);
+    const double zstd = sqrt(sv / Ns);
+    const double norm = s1 / Ns;                  // likelihood.py:111
+    const double neff = s1 * s1 / s2;             // likelihood.py:112
+    const bool ok = (a.kind == CHB_PGW_FULL) ? !(neff < a.pe_neff) : (neff >= a.pe_neff);
+
+    double* pout = nullptr;
+    if (a.p_gw_out) pout = a.p_gw_out + ((size_t)h * a.Nev + ev) * (size_t)(pixelated ? Pp : 1) * Nz;
+    const int npix = pixelated ? a.neff_pix[ev] : 1;
+
+    if (!ok) {                                    // lax.cond false branch: zeros
+      if (pout) for (int i = tid; i < (pixelated ? Pp : 1) * Nz; i += NUM_THREADS) pout[i] = 0.0;
+      if (tid == 0) { a.log_like[(size_t)h * a.Nev + ev] = nan_to_num_log(0.0); a.like_raw[(size_t)h * a.Nev + ev] = 0.0; }
+      continue;
+    }
+
+    // ---- effective grid (likelihood.py:115-123 / 186-190) -----------------------------
+    int G = Nz;
+    if (a.kind != CHB_PGW_FULL) {
+      if (a.use_cut) {
+        G = Nz / 2;
+        const double lb = (zmn - a.cut_grid * zstd > 0.0) ? zmn - a.cut_grid * zstd : 1.e-8;
+        const double ub = zmx + a.cut_grid * zstd;
+        const double step = (ub - lb) / (double)(G - 1);
+        for (int i = tid; i < G; i += NUM_THREADS) eg[i] = (i == G - 1) ? ub : __dadd_rn(__dmul_rn((double)i, step), lb);
+      } else {
+        for (int i = tid; i < G; i += NUM_THREADS) eg[i] = zgrid[i];
+      }
+    }
+    __syncthreads();
+
+    double like_acc = 0.0;      // per-thread partial of sum_p trapz_k(...)
+    const double fR = HC[HC_FR];
+    const double* pcat_ev = has_cat ? a.p_cat + (size_t)ev * Pp * Nz : nullptr;
+    const double* pcompl_ev = has_cat ? a.P_compl + (size_t)ev * Nz : nullptr;
+
+    if (a.kind == CHB_PGW_1D || a.kind == CHB_PGW_APPROX) {
+      // ---- p_gw1d ------------------------------------------------------------------------
+      const double* dx = zs;
+      const double* dw = ws;
+      int dn = Ns;
+      double W = s1, Q = s2, dstd = zstd;
+      if (a.binning) {                           // utils/math.py:32-46
+        const double step = (zmx - zmn) / (double)B;
+        for (int i = tid; i < B; i += NUM_THREADS) {
+          double e0 = __dadd_rn(__dmul_rn((double)i, step), zmn);
+          double e1 = (i + 1 == B) ? zmx : __dadd_rn(__dmul_rn((double)(i + 1), step), zmn);
+          bc[i] = (e0 + e1) / 2;
+          bs[i] = 0.0;
+        }
+        __syncthreads();
+        for (int j = tid; j < Ns; j += NUM_THREADS) {
+          double f = floor((zs[j] - zmn) / (zmx - zmn) * B);
+          if (!isnan(f)) atomicAdd(&bs[(int)fmin(fmax(f, 0.0), (double)(B - 1))], ws[j]);
+        }
+        __syncthreads();
+        double t1 = 0, t2 = 0, tc = 0;
+        for (int i = tid; i < B; i += NUM_THREADS) { t1 += bs[i]; t2 += bs[i] * bs[i]; tc += bc[i]; }
+        W = block_sum(t1, red); Q = block_sum(t2, red);
+        const double cmean = block_sum(tc, red) / B;
+        double tv = 0;
+        for (int i = tid; i < B; i += NUM_THREADS) { double d = bc[i] - cmean; tv += d * d; }
+        dstd = sqrt(block_sum(tv, red) / B);
+        dx = bc; dw = bs; dn = B;
+      }
+      const double neff_k = 1.0 / (Q / (W * W));                     // 1/sum((w/W)^2)
+      double bw;
+      if (a.bw_method == CHB_BW_SCOTT) bw = pow(neff_k, -0.2) * dstd;
+      else if (a.bw_method == CHB_BW_SILVERMAN) bw = pow(neff_k * 3.0 / 4.0, -0.2) * dstd;
+      else bw = a.bw_value * dstd;
+      kde1d_f64(dx, dw, dn, eg, G, bw, a.kernel, norm / (W * bw), dens);
+      __syncthreads();
+      for (int k = tid; k < Nz; k += NUM_THREADS) pgw[k] = interp_lr(zgrid[k], eg, dens, G, 0.0, 0.0);
+      __syncthreads();
+      if (a.kind == CHB_PGW_1D) {
+        for (int k = tid; k < Nz; k += NUM_THREADS) {
+          const double pz = dV[k] * rj[k];
+          like_acc += (pgw[k] * pz / jac[k]) * tw[k];
+          if (pout) pout[k] = pgw[k];
+        }
+      } else {
+        const double* gwp = a.gw_pdf + (size_t)ev * Pp;
+        if (pout) for (int i = tid; i < Pp * Nz; i += NUM_THREADS) pout[i] = pgw[i % Nz] * gwp[i / Nz];
+        for (int i = tid; i < npix * Nz; i += NUM_THREADS) {
+          const int p = i / Nz, k = i - p * Nz;
+          const double pc = has_cat ? pcat_ev[(size_t)p * Nz + k] : 0.0;
+          if (pc == -100.0) continue;            // likelihood.py:274 sentinel mask
+          const double pgal = has_cat ? fR * pc + (1.0 - pcompl_ev[k]) * dV[k] : dV[k];
+          const double pz = pgal * rj[k];
+          like_acc += ((pgw[k] * gwp[p]) * pz / jac[k]) * tw[k];
+        }
+      }
+    } else if (a.kind == CHB_PGW_MARG) {
+      // ---- p_gw3dmarg (always Epanechnikov, likelihood.py:192) ----------------------------
+      const int* off = a.pix_off + (size_t)ev * (Pp + 2);
+      const double* gwp = a.gw_pdf + (size_t)ev * Pp;
+      if (pout) for (int i = tid; i < Pp * Nz; i += NUM_THREADS) pout[i] = 0.0;
+      for (int p = 0; p < npix; ++p) {
+        const int o0 = off[p], o1 = off[p + 1], nin = o1 - o0;
+        double t1 = 0, t2 = 0, tz = 0, tm = -INFINITY;
+        for (int j = o0 + tid; j < o1; j += NUM_THREADS) { double w = ws[j]; t1 += w; t2 += w * w; tz += zs[j]; tm = fmax(tm, zs[j]); }
+        double W = block_sum(t1, red), Q = block_sum(t2, red);
+        const double zsum = block_sum(tz, red);
+        const double zmax_in = fmax(block_max(tm, red), zmn);       // masked samples sit at min(z)
+        const double* dx = zs + o0;
+        const double* dw = ws + o0;
+        int dn = nin;
+        double dstd;
+        if (a.binning) {
+          const double step = (zmax_in - zmn) / (double)B;
+          for (int i = tid; i < B; i += NUM_THREADS) {
+            double e0 = __dadd_rn(__dmul_rn((double)i, step), zmn);
+            double e1 = (i + 1 == B) ? zmax_in : __dadd_rn(__dmul_rn((double)(i + 1), step), zmn);
+            bc[i] = (e0 + e1) / 2;
+            bs[i] = 0.0;
+          }
+          __syncthreads();
+          for (int j = o0 + tid; j < o1; j += NUM_THREADS) {
+            double f = floor((zs[j] - zmn) / (zmax_in - zmn) * B);
+            if (!isnan(f)) atomicAdd(&bs[(int)fmin(fmax(f, 0.0), (double)(B - 1))], ws[j]);
+          }
+          __syncthreads();
+          double u1 = 0, u2 = 0, uc = 0;
+          for (int i = tid; i < B; i += NUM_THREADS) { u1 += bs[i]; u2 += bs[i] * bs[i]; uc += bc[i]; }
+          W = block_sum(u1, red); Q = block_sum(u2, red);
+          const double cmean = block_sum(uc, red) / B;
+          double tv = 0;
+          for (int i = tid; i < B; i += NUM_THREADS) { double d = bc[i] - cmean; tv += d * d; }
+          dstd = sqrt(block_sum(tv, red) / B);
+          dx = bc; dw = bs; dn = B;
+        } else {
+          // std of the masked data set: in-pixel samples + (Ns - nin) copies of min(z)
+          const double mm_ = (zsum + (double)(Ns - nin) * zmn) / Ns;
+          double tv = 0;
+          for (int j = o0 + tid; j < o1; j += NUM_THREADS) { double d = zs[j] - mm_; tv += d * d; }
+          tv = block_sum(tv, red) + (double)(Ns - nin) * (zmn - mm_) * (zmn - mm_);
+          dstd = sqrt(tv / Ns);
+        }
+        const double neff_k = 1.0 / (Q / (W * W));
+        double bw;
+        if (a.bw_method == CHB_BW_SCOTT) bw = pow(neff_k, -0.2) * dstd;
+        else if (a.bw_method == CHB_BW_SILVERMAN) bw = pow(neff_k * 3.0 / 4.0, -0.2) * dstd;
+        else bw = a.bw_value * dstd;
+        // W == 0 (no weight in the pixel) -> w/W = NaN for every sample in the reference
+        const double scale = (W != 0.0) ? (norm * gwp[p]) / (W * bw) : nan("");
+        kde1d_f64(dx, dw, dn, eg, G, bw, CHB_KERNEL_EPAN, 1.0, dens);
+        __syncthreads();
+        for (int k = tid; k < Nz; k += NUM_THREADS) {
+          const double raw = interp_lr(zgrid[k], eg, dens, G, 0.0, 0.0);
+          const double inside = (zgrid[k] >= eg[0] && zgrid[k] <= eg[G - 1]);
+          const double v = inside ? raw * scale : 0.0;          // interp(left=0,right=0) of kde*... then *norm*gw_pdf
+          const double pc = has_cat ? pcat_ev[(size_t)p * Nz + k] : 0.0;
+          if (pout) pout[(size_t)p * Nz + k] = v;
+          if (pc == -100.0) continue;
+          const double pgal = has_cat ? fR * pc + (1.0 - pcompl_ev[k]) * dV[k] : dV[k];
+          like_acc += (v * (pgal * rj[k]) / jac[k]) * tw[k];
+        }
+        __syncthreads();
+      }
+    } else {
+      // ---- p_gw3dfull: 3-D whitened Gaussian KDE (likelihood.py:211-260, math.py:154-229) --
+      const double* ra = a.ra + so;
+      const double* dec = a.dec + so;
+      const double W = s1;
+      const double Qn = s2 / (W * W);                 // sum of squared normalised weights
+      const double neff_k = 1.0 / Qn;
+      double factor;
+      if (a.bw_method == CHB_BW_SCOTT) factor = pow(neff_k, -1.0 / 7.0);
+      else if (a.bw_method == CHB_BW_SILVERMAN) factor = pow(neff_k * 5.0 / 4.0, -1.0 / 7.0);
+      else factor = a.bw_value;
+      double m0 = 0, m1 = 0, m2 = 0;
+      for (int j = tid; j < Ns; j += NUM_THREADS) { double wn = ws[j] / W; m0 += wn * zs[j]; m1 += wn * ra[j]; m2 += wn * dec[j]; }
+      m0 = block_sum(m0, red); m1 = block_sum(m1, red); m2 = block_sum(m2, red);
+      double c00 = 0, c01 = 0, c02 = 0, c11 = 0, c12 = 0, c22 = 0;
+      for (int j = tid; j < Ns; j += NUM_THREADS) {
+        double wn = ws[j] / W, r0 = zs[j] - m0, r1 = ra[j] - m1, r2 = dec[j] - m2;
+        c00 += wn * r0 * r0; c01 += wn * r0 * r1; c02 += wn * r0 * r2;
+        c11 += wn * r1 * r1; c12 += wn * r1 * r2; c22 += wn * r2 * r2;
+      }
+      c00 = block_sum(c00, red); c01 = block_sum(c01, red); c02 = block_sum(c02, red);
+      c11 = block_sum(c11, red); c12 = block_sum(c12, red); c22 = block_sum(c22, red);
+      if (tid == 0) {
+        const double dn_ = 1.0 - Qn;
+        c00 /= dn_; c01 /= dn_; c02 /= dn_; c11 /= dn_; c12 /= dn_; c22 /= dn_;
+        // inverse of the symmetric 3x3 covariance, / factor^2
+        const double a00 = c11 * c22 - c12 * c12, a01 = c02 * c12 - c01 * c22, a02 = c01 * c12 - c02 * c11;
+        const double a11 = c00 * c22 - c02 * c02, a12 = c01 * c02 - c00 * c12, a22 = c00 * c11 - c01 * c01;
+        const double det = c00 * a00 + c01 * a01 + c02 * a02;
+        const double f2 = factor * factor;
+        const double i00 = a00 / det / f2, i01 = a01 / det / f2, i02 = a02 / det / f2;
+        const double i11 = a11 / det / f2, i12 = a12 / det / f2, i22 = a22 / det / f2;
+        // lower Cholesky factor of inv_cov
+        const double l00 = sqrt(i00), l10 = i01 / l00, l20 = i02 / l00;
+        const double l11 = sqrt(i11 - l10 * l10), l21 = (i12 - l20 * l10) / l11;
+        const double l22 = sqrt(i22 - l20 * l20 - l21 * l21);
+        L[0] = l00; L[1] = l10; L[2] = l11; L[3] = l20; L[4] = l21; L[5] = l22;
+        L[6] = log(l00) + log(l11) + log(l22) - 1.5 * log(2.0 * CHB_PI);
+      }
+      __syncthreads();
+      const double l00 = L[0], l10 = L[1], l11 = L[2], l20 = L[3], l21 = L[4], l22 = L[5], lognorm = L[6];
+      // whiten samples about the weighted mean: y = (x - mu)^T L ; weights normalised in place
+      for (int j = tid; j < Ns; j += NUM_THREADS) {
+        const double r0 = zs[j] - m0, r1 = ra[j] - m1, r2 = dec[j] - m2;
+        zs[j] = r0 * l00 + r1 * l10 + r2 * l20;
+        y1[j] = r1 * l11 + r2 * l21;
+        y2[j] = r2 * l22;
+        ws[j] = ws[j] / W;
+      }
+      if (pout) for (int i = tid; i < Pp * Nz; i += NUM_THREADS) pout[i] = 0.0;
+      __syncthreads();
+      const double zlo = zmn - a.cut_grid * zstd, zhi = zmx + a.cut_grid * zstd;   // likelihood.py:225
+      const double* rap = a.ra_pix + (size_t)ev * Pp;
+      const double* dep = a.dec_pix + (size_t)ev * Pp;
+      for (int i = warp; i < npix * Nz; i += NUM_WARPS) {
+        const int p = i / Nz, k = i - p * Nz;
+        const double z = zgrid[k];
+        if (!(z <= zhi && z >= zlo)) continue;
+        const double r0 = z - m0, r1 = rap[p] - m1, r2 = dep[p] - m2;
+        const double q0 = r0 * l00 + r1 * l10 + r2 * l20, q1 = r1 * l11 + r2 * l21, q2 = r2 * l22;
+        double acc = 0.0;
+        for (int j = lane; j < Ns; j += 32) {
+          const double d0 = zs[j] - q0, d1 = y1[j] - q1, d2 = y2[j] - q2;
+          acc += ws[j] * exp(lognorm - 0.5 * (d0 * d0 + d1 * d1 + d2 * d2));
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) {
+          const double v = acc * norm;
+          if (pout) pout[(size_t)p * Nz + k] = v;
+          const double pc = has_cat ? pcat_ev[(size_t)p * Nz + k] : 0.0;
+          if (pc != -100.0) {
+            const double pgal = has_cat ? fR * pc + (1.0 - pcompl_ev[k]) * dV[k] : dV[k];
+            like_acc += (v * (pgal * rj[k]) / jac[k]) * tw[k];
+          }
+        }
+      }
+    }
+
+    const double like = block_sum(like_acc, red);
+    if (tid == 0) { a.log_like[(size_t)h * a.Nev + ev] = nan_to_num_log(like); a.like_raw[(size_t)h * a.Nev + ev] = like; }
+  }
+}
+
+cudaError_t numerator_configure(size_t smem) {
+  return cudaFuncSetAttribute(numerator_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+cudaError_t launch_numerator(const NumArgs& a, int grid, int block, size_t smem, cudaStream_t s) {
+  numerator_kernel<<<grid, block, smem, s>>>(a);
+  return cudaGetLastError();
+}

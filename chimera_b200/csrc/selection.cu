@@ -1,0 +1,110 @@
+// selection.cu -- injection-reweighted Monte-Carlo selection function (kernel 1).
+//
+// For every (injection, hyper-point) pair: dN/dtheta_det of the population at the injection
+// (CHIMERA/population/pop_wrapper.py:102-111) divided by p_draw, reduced to the two sums
+// selection_function.N_exp needs (CHIMERA/selection_function.py:37-44):
+//     S1 = nansum(w),  S2 = sum(w^2),   w = R0 p(m1s,m2s) dVc/dz psi(z)/(1+z) / (|ddL/dz| (1+z)^2 p_draw)
+// Grid = (injection tiles, hyper-points).  Each CTA stages its hyper-point's table block in
+// shared memory with one TMA bulk copy, streams a contiguous tile of the four injection arrays
+// with coalesced 8-byte loads, and writes one (S1,S2) pair; reduce.cu adds the tiles in a fixed
+// order, so results are bit-reproducible run to run.  fp64 throughout.
+#include "common.cuh"
+#include "stage.cuh"
+
+__global__ void __launch_bounds__(256)
+selection_kernel(SelArgs a) {
+  extern __shared__ __align__(16) double sm[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ double P[CHB_NPAR];
+  __shared__ double HC[CHB_NHC];
+  __shared__ double red[32];
+  const TableLayout lay = a.mc.lay;
+  const int h = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
+  const uint32_t tab_bytes = (uint32_t)(lay.total() * sizeof(double));
+
+  if (tid == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&bar, tab_bytes);
+    bulk_g2s(sm, a.tabs + (size_t)h * lay.total(), tab_bytes, &bar);
+  }
+  if (tid < CHB_NPAR) P[tid] = a.hyper[(size_t)h * CHB_NPAR + tid];
+  if (tid < CHB_NHC) HC[tid] = a.HC[(size_t)h * CHB_NHC + tid];
+  __syncthreads();
+  mbar_wait(&bar, 0);
+
+  const double* zg = sm + lay.off_zg();
+  const double* dLt = sm + lay.off_dLt();
+  const double* mg = sm + lay.off_mg();
+  const double* cdf = sm + lay.off_cdf();
+  const int rc = lay.rc, rm = lay.rm;
+  const int cm = a.mc.cosmo_model, mm = a.mc.mass_model, rmod = a.mc.rate_model;
+  const double R0 = P[CHB_P_R0];
+
+  const long long chunk = ((long long)a.Ninj + a.tiles - 1) / a.tiles;
+  const long long j0 = (long long)tile * chunk;
+  const long long j1 = min((long long)a.Ninj, j0 + chunk);
+  double s1 = 0.0, s2 = 0.0;
+  for (long long j = j0 + tid; j < j1; j += blockDim.x) {
+    const double dL = __ldg(a.dL + j), m1d = __ldg(a.m1d + j), m2d = __ldg(a.m2d + j), pd = __ldg(a.p_draw + j);
+    const double z = interp_clamped(dL, dLt, zg, rc);                  // z_from_dGW
+    const double opz = 1.0 + z;
+    const double m1 = m1d / opz, m2 = m2d / opz;                      // theta_det2src
+    const double dCt = dL2dCt(cm, P, dL, z);                          // original distances
+    const double Ez = E_at_z(P, HC, z);
+    const double pz = dVcdz_from(HC, dCt, Ez) * (merger_rate(rmod, P, HC, z) / opz);
+    const double dN = R0 * p_m1m2(mm, P, HC, mg, cdf, rm, m1, m2) * pz;
+    const double jac = fabs(ddLdz_from(cm, P, HC, z, dCt, Ez)) * (opz * opz);
+    const double w = (dN / jac) / pd;
+    if (!isnan(w)) s1 += w;     // nansum for xi (selection_function.py:39)
+    s2 += w * w;                // plain sum for the variance (:44)
+  }
+  s1 = block_sum(s1, red);
+  s2 = block_sum(s2, red);
+  if (tid == 0) {
+    double* out = a.tile_part + ((size_t)h * a.tiles + tile) * 2;
+    out[0] = s1;
+    out[1] = s2;
+  }
+}
+
+cudaError_t launch_selection(const SelArgs& a, cudaStream_t s) {
+  size_t smem = (size_t)a.mc.lay.total() * sizeof(double);
+  cudaError_t e = cudaFuncSetAttribute(selection_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  dim3 grid(a.tiles, a.n_hyper);
+  selection_kernel<<<grid, 256, smem, s>>>(a);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// reduce: per hyper-point, sum log-likelihoods over events and (S1,S2) over injection tiles in a
+// fixed order -> partials (n_hyper, 3).  -DBL_MAX entries overflow to -inf when two or more are
+// present, exactly like the reference's jnp.sum over nan_to_num'ed values (likelihood.py:297-298).
+__global__ void __launch_bounds__(256)
+reduce_kernel(int n_hyper, int Nev, int tiles, const double* __restrict__ log_like,
+              const double* __restrict__ tile_part, double* __restrict__ partials) {
+  __shared__ double red[32];
+  const int h = blockIdx.x, tid = threadIdx.x;
+  double s = 0.0;
+  if (log_like) for (int e = tid; e < Nev; e += blockDim.x) s += log_like[(size_t)h * Nev + e];
+  s = block_sum(s, red);
+  double s1 = 0.0, s2 = 0.0;
+  if (tile_part) for (int t = tid; t < tiles; t += blockDim.x) {
+    s1 += tile_part[((size_t)h * tiles + t) * 2];
+    s2 += tile_part[((size_t)h * tiles + t) * 2 + 1];
+  }
+  s1 = block_sum(s1, red);
+  s2 = block_sum(s2, red);
+  if (tid == 0) {
+    partials[(size_t)h * 3 + 0] = s;
+    partials[(size_t)h * 3 + 1] = s1;
+    partials[(size_t)h * 3 + 2] = s2;
+  }
+}
+
+cudaError_t launch_reduce(int n_hyper, int Nev, int tiles, const double* d_log_like, const double* d_tile_part,
+                          double* d_partials, cudaStream_t s) {
+  reduce_kernel<<<n_hyper, 256, 0, s>>>(n_hyper, Nev, tiles, d_log_like, d_tile_part, d_partials);
+  return cudaGetLastError();
+}

@@ -1,0 +1,204 @@
+// tables.cu -- per-hyper-point interpolation tables (kernel 0).
+//
+// One CTA per hyper-point rebuilds what `population.update(**hyper_lambdas)` rebuilds in the
+// reference for every likelihood call:
+//   cosmology: z_grid_interp = [0] U logspace(-10, log10 z_max, res-1), integral_invE_interp =
+//              cumtrapz(1/E, z)                               (population/cosmo.py:43-46)
+//              + the dL(z) table z_from_dGW inverts            (cosmo.py:260-264)
+//   mass:      m_grid = logspace(log10 m_low, log10 m_high, res), cdf_m2_conditioned =
+//              cumtrapz(p2(m_grid | m1 = m_high)), norm_p_m1 = trapz(p1(m_grid))   (mass.py:45-52)
+// plus the scalar constants (HC row) the other kernels reuse.  fp64 throughout; the two prefix
+// sums are sequential (one thread each, different warps) so they associate exactly like
+// numpy's cumsum -- ~25 us per CTA, all hyper-points in parallel, negligible next to the KDE.
+#include "common.cuh"
+
+__global__ void __launch_bounds__(256)
+build_tables_kernel(ModelCfg mc, int n_hyper, const double* __restrict__ hyper, double* __restrict__ tabs,
+                    double* __restrict__ HCg) {
+  extern __shared__ double sm[];
+  const int rc = mc.lay.rc, rm = mc.lay.rm;
+  double* zs = sm;            // rc
+  double* ys = zs + rc;       // rc : 1/E, then integral_invE in place
+  double* p2 = ys + rc;       // rm : secondary pdf at m1 = m_high, then cdf in place
+  double* p1 = p2 + rm;       // rm : primary pdf
+  double* ms = p1 + rm;       // rm : m_grid
+  __shared__ double P[CHB_NPAR];
+  __shared__ double HC[CHB_NHC];
+
+  const int h = blockIdx.x;
+  if (h >= n_hyper) return;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (tid < CHB_NPAR) P[tid] = hyper[(size_t)h * CHB_NPAR + tid];
+  if (tid < CHB_NHC) HC[tid] = 0.0;
+  __syncthreads();
+
+  if (tid == 0) {
+    HC[HC_DH] = 299792.458e-3 / P[CHB_P_H0];
+    HC[HC_ODE0] = 1.0 - P[CHB_P_OM0] - P[CHB_P_OR0] - P[CHB_P_OK0];
+    HC[HC_SQRTOK] = sqrt(fabs(P[CHB_P_OK0] + 1.e-10));
+    HC[HC_DE_CONST] = (P[CHB_P_W0] == -1.0 && P[CHB_P_WA] == 0.0) ? 1.0 : 0.0;
+    const double lo = P[CHB_P_MLOW], hi = P[CHB_P_MHIGH];
+    HC[HC_LOG10_MLOW] = log10(lo);
+    HC[HC_DLOG10_M] = (log10(hi) - log10(lo)) / (double)(rm - 1);
+    HC[HC_LOG10_ZSTEP] = (log10(P[CHB_P_ZMAX]) + 10.0) / (double)(rc - 2);
+    if (mc.mass_model == CHB_MASS_PLP) {
+      double a = -P[CHB_P_ALPHA];
+      HC[HC_PL_NORM] = (a == -1.0) ? (log(lo) - log(hi)) : (pow(hi, 1.0 + a) - pow(lo, 1.0 + a)) / (1.0 + a);
+      double mu = P[CHB_P_MUG], sg = P[CHB_P_SIGMAG];
+      double up = ((mu + 5.0 * sg) - mu) / (sg * sqrt(2.0));
+      double dn = (lo - mu) / (sg * sqrt(2.0));
+      HC[HC_TG_NORM] = 0.5 * erf(up) - 0.5 * erf(dn);
+    } else if (mc.mass_model == CHB_MASS_BPL) {
+      double mb = lo + P[CHB_P_BREAKF] * (hi - lo);
+      HC[HC_MBREAK] = mb;
+      HC[HC_BPL_RATIO] = tpl_notnorm(mb, -P[CHB_P_ALPHA], lo, mb) / tpl_notnorm(mb, -P[CHB_P_ALPHA2], mb, hi);
+    }
+    double g = P[CHB_P_GAMMA];
+    if (mc.rate_model == CHB_RATE_MADAU_DICKINSON || mc.rate_model == CHB_RATE_TRUNC_MD)
+      HC[HC_RATE_NORM] = 1.0 + pow(1.0 + P[CHB_P_ZP], -g - P[CHB_P_KAPPA]);
+    else if (mc.rate_model == CHB_RATE_TRUNC_PL)
+      HC[HC_RATE_NORM] = 1.0 / ((pow(1.0 + P[CHB_P_RZMAX], g + 1.0) - 1.0) / (g + 1.0));
+    HC[HC_NORM_P_M1] = 1.0;
+  }
+  __syncthreads();
+
+  // knots (numpy.linspace: arange*step + start, last = stop; then 10**y)
+  const double lzmax = log10(P[CHB_P_ZMAX]);
+  const double zstep = (lzmax - (-10.0)) / (double)(rc - 2);
+  for (int i = tid; i < rc; i += nt) {
+    double z = 0.0;
+    if (i > 0) {
+      double y = (i - 1 == rc - 2) ? lzmax : __dadd_rn(__dmul_rn((double)(i - 1), zstep), -10.0);
+      z = pow(10.0, y);
+    }
+    zs[i] = z;
+    ys[i] = 1.0 / E_at_z(P, HC, z);
+  }
+  const double l0 = log10(P[CHB_P_MLOW]), l1 = log10(P[CHB_P_MHIGH]);
+  const double mstep = (l1 - l0) / (double)(rm - 1);
+  for (int i = tid; i < rm; i += nt) {
+    double y = (i == rm - 1) ? l1 : __dadd_rn(__dmul_rn((double)i, mstep), l0);
+    double m = pow(10.0, y);
+    ms[i] = m;
+    p2[i] = secondary_notnorm(mc.mass_model, P, m, P[CHB_P_MHIGH]);
+    p1[i] = primary_notnorm(mc.mass_model, P, HC, m);
+  }
+  __syncthreads();
+
+  if (tid == 0) {            // cumtrapz(1/E, z)  (utils/math.py:22-26)
+    double prev = ys[0], acc = 0.0;
+    ys[0] = 0.0;
+    for (int i = 1; i < rc; ++i) {
+      double cur = ys[i];
+      acc += 0.5 * (prev + cur) * (zs[i] - zs[i - 1]);
+      ys[i] = acc;
+      prev = cur;
+    }
+  } else if (tid == 32) {    // cumtrapz(p2) and trapz(p1)
+    double prev = p2[0], acc = 0.0, nrm = 0.0;
+    p2[0] = 0.0;
+    for (int i = 1; i < rm; ++i) {
+      double cur = p2[i], dx = ms[i] - ms[i - 1];
+      acc += 0.5 * (prev + cur) * dx;
+      p2[i] = acc;
+      prev = cur;
+      nrm += dx * (p1[i] + p1[i - 1]) / 2.0;
+    }
+    HC[HC_NORM_P_M1] = nrm;
+  }
+  __syncthreads();
+
+  double* T = tabs + (size_t)h * mc.lay.total();
+  for (int i = tid; i < rc; i += nt) {
+    double z = zs[i];
+    double dCt = dCt_from_dCr(P, HC, HC[HC_DH] * ys[i]);
+    double dL = dCt * (1.0 + z);
+    if (mc.cosmo_model == CHB_COSMO_MG_FLRW) dL *= Xi_at_z(P, z);
+    T[mc.lay.off_zg() + i] = z;
+    T[mc.lay.off_iinv() + i] = ys[i];
+    T[mc.lay.off_dLt() + i] = dL;
+  }
+  for (int i = tid; i < rm; i += nt) {
+    T[mc.lay.off_mg() + i] = ms[i];
+    T[mc.lay.off_cdf() + i] = p2[i];
+  }
+  if (tid == 0 && mc.catalog_kind == 1) {   // fR = Vc(z_hi) - Vc(z_lo)  (completeness.py:54-58)
+    double dlo = dCt_from_dCr(P, HC, HC[HC_DH] * interp_clamped(mc.compl_z_lo, zs, ys, rc));
+    double dhi = dCt_from_dCr(P, HC, HC[HC_DH] * interp_clamped(mc.compl_z_hi, zs, ys, rc));
+    HC[HC_FR] = Vc_from_dCt(P, HC, dhi) - Vc_from_dCt(P, HC, dlo);
+  }
+  __syncthreads();
+  if (tid < CHB_NHC) HCg[(size_t)h * CHB_NHC + tid] = HC[tid];
+}
+
+cudaError_t launch_build_tables(const ModelCfg& mc, int n_hyper, const double* d_hyper, double* d_tabs,
+                                double* d_HC, cudaStream_t s) {
+  size_t smem = (size_t)(2 * mc.lay.rc + 3 * mc.lay.rm) * sizeof(double);
+  cudaError_t e = cudaFuncSetAttribute(build_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  build_tables_kernel<<<n_hyper, 256, smem, s>>>(mc, n_hyper, d_hyper, d_tabs, d_HC);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// element-wise plug-in functions for one parameter row (chb_model_eval)
+__global__ void model_eval_kernel(ModelCfg mc, int which, const double* __restrict__ P, const double* __restrict__ T,
+                                  const double* __restrict__ HC, long long n, const double* __restrict__ a,
+                                  const double* __restrict__ b, const double* __restrict__ c, double* __restrict__ out) {
+  const int rc = mc.lay.rc, rm = mc.lay.rm;
+  const double* zg = T + mc.lay.off_zg();
+  const double* iinv = T + mc.lay.off_iinv();
+  const double* dLt = T + mc.lay.off_dLt();
+  const double* mg = T + mc.lay.off_mg();
+  const double* cdf = T + mc.lay.off_cdf();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double x = a[i], r = 0.0;
+    switch (which) {
+      case CHB_F_E_AT_Z: r = E_at_z(P, HC, x); break;
+      case CHB_F_DCT_AT_Z: r = dCt_from_dCr(P, HC, HC[HC_DH] * interp_clamped(x, zg, iinv, rc)); break;
+      case CHB_F_DL_AT_Z: {
+        r = dCt_from_dCr(P, HC, HC[HC_DH] * interp_clamped(x, zg, iinv, rc)) * (1.0 + x);
+        if (mc.cosmo_model == CHB_COSMO_MG_FLRW) r *= Xi_at_z(P, x);
+      } break;
+      case CHB_F_Z_FROM_DGW: r = interp_clamped(x, dLt, zg, rc); break;
+      case CHB_F_DDLDZ_AT_Z:
+      case CHB_F_DVCDZ_AT_Z:
+      case CHB_F_VC_AT_Z: {
+        double dCt = b ? dL2dCt(mc.cosmo_model, P, b[i], x)
+                       : dCt_from_dCr(P, HC, HC[HC_DH] * interp_clamped(x, zg, iinv, rc));
+        if (which == CHB_F_VC_AT_Z) r = Vc_from_dCt(P, HC, dCt);
+        else {
+          double Ez = E_at_z(P, HC, x);
+          r = (which == CHB_F_DDLDZ_AT_Z) ? ddLdz_from(mc.cosmo_model, P, HC, x, dCt, Ez) : dVcdz_from(HC, dCt, Ez);
+        }
+      } break;
+      case CHB_F_P_M1M2: r = p_m1m2(mc.mass_model, P, HC, mg, cdf, rm, x, b[i]); break;
+      case CHB_F_P_M1_NOTNORM: r = primary_notnorm(mc.mass_model, P, HC, x); break;
+      case CHB_F_MERGER_RATE: r = merger_rate(mc.rate_model, P, HC, x); break;
+      case CHB_F_POP_RATE_DET_INJ: {   // pop_wrapper.py:102-111 ; a=m1det b=m2det c=dL
+        double dL = c[i];
+        double z = interp_clamped(dL, dLt, zg, rc);
+        double m1 = x / (1.0 + z), m2 = b[i] / (1.0 + z);
+        double dCt = dL2dCt(mc.cosmo_model, P, dL, z);
+        double Ez = E_at_z(P, HC, z);
+        double pz = dVcdz_from(HC, dCt, Ez) * (merger_rate(mc.rate_model, P, HC, z) / (1.0 + z));
+        double dN = P[CHB_P_R0] * p_m1m2(mc.mass_model, P, HC, mg, cdf, rm, m1, m2) * pz;
+        double jac = fabs(ddLdz_from(mc.cosmo_model, P, HC, z, dCt, Ez)) * ((1.0 + z) * (1.0 + z));
+        r = dN / jac;
+      } break;
+      default: r = nan(""); break;
+    }
+    out[i] = r;
+  }
+}
+
+cudaError_t launch_model_eval(const ModelCfg& mc, int which, const double* d_params, const double* d_tabs,
+                              const double* d_HC, long long n, const double* a, const double* b, const double* c,
+                              double* out, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  int block = 256;
+  long long grid = (n + block - 1) / block;
+  if (grid > 148 * 16) grid = 148 * 16;
+  model_eval_kernel<<<(int)grid, block, 0, s>>>(mc, which, d_params, d_tabs, d_HC, n, a, b, c, out);
+  return cudaGetLastError();
+}

@@ -1,0 +1,257 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (ctypes) and the Python
+mirror of the reference interface, against (a) the golden fixtures produced by the reference
+source and (b) the NumPy oracle on seeded synthetic inputs.
+
+Tolerances (BASELINE.json north_star): per-event and total log-likelihoods to 1e-5 relative in
+fp64 mode and 1e-3 in fp32 mode.  The fp64 assertions below are far tighter (1e-9) because the
+fp64 kernels follow the reference operation by operation."""
+import numpy as np
+import pytest
+
+from cases import COSMO_CASES, MASS_CASES, RATE_CASES, LIKE_CASES, GOLDEN_NUM_BINS
+
+pytestmark = pytest.mark.gpu
+
+RTOL64 = 1e-9      # asserted in fp64 mode (required: 1e-5)
+RTOL32 = 1e-3      # fp32 mode requirement
+RTOL32_TIGHT = 2e-5  # what the fp32 pair sums actually deliver on these cases
+
+
+@pytest.fixture(scope="module")
+def cb():
+  import chimera_b200
+  from chimera_b200 import _lib
+  if _lib.device_count() == 0:
+    pytest.fail("no CUDA device: the gpu-marked tests must run on the B200 box")
+  return chimera_b200
+
+
+def close(a, b, rtol, atol=0.0):
+  np.testing.assert_allclose(np.asarray(a), np.asarray(b), rtol=rtol, atol=atol, equal_nan=True)
+
+
+def same_class(a, b, rtol):
+  a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+  fin = np.isfinite(a) & (np.abs(a) < 1e300)
+  assert np.array_equal(fin, np.isfinite(b) & (np.abs(b) < 1e300))
+  np.testing.assert_allclose(a[fin], b[fin], rtol=rtol)
+  assert np.array_equal(a[~fin], b[~fin])
+
+
+COSMO_CLS = {"flrw": "flrw", "mg_flrw": "mg_flrw"}
+MASS_CLS = {"tpl": "tpl", "bpl": "bpl", "plp": "plp"}
+
+
+@pytest.mark.parametrize("i", range(len(COSMO_CASES)))
+def test_cosmology_functions(cb, golden_models, i):
+  g = golden_models
+  model, kw = COSMO_CASES[i]
+  c = getattr(cb.cosmo, model)(**kw)
+  z = g["z"]
+  close(np.stack([c.z_grid_interp, c.integral_invE_interp]), g[f"cosmo{i}_tab"], 1e-12, 1e-300)
+  close(cb.cosmo.E_at_z(c, z), g[f"cosmo{i}_E"], 1e-12)
+  close(cb.cosmo.dL_at_z(c, z), g[f"cosmo{i}_dL"], 1e-11)
+  close(cb.cosmo.ddLdz_at_z(c, z), g[f"cosmo{i}_ddL"], 1e-11)
+  close(cb.cosmo.dVcdz_at_z(c, z), g[f"cosmo{i}_dV"], 1e-11)
+  close(cb.cosmo.Vc_at_z(c, z), g[f"cosmo{i}_Vc"], 1e-10, 1e-40)
+  dq = g[f"cosmo{i}_dq"]
+  zq = cb.cosmo.z_from_dGW(c, dq)
+  close(zq, g[f"cosmo{i}_zq"], 1e-11)
+  close(cb.cosmo.ddLdz_at_z(c, g[f"cosmo{i}_zq"], dq), g[f"cosmo{i}_ddL_dist"], 1e-11)
+  close(cb.cosmo.dVcdz_at_z(c, g[f"cosmo{i}_zq"], dq), g[f"cosmo{i}_dV_dist"], 1e-11)
+
+
+@pytest.mark.parametrize("i", range(len(MASS_CASES)))
+def test_mass_functions(cb, golden_models, i):
+  g = golden_models
+  model, kw = MASS_CASES[i]
+  m = getattr(cb.mass, model)(**kw)
+  close(m.norm_p_m1, g[f"mass{i}_norm"], 1e-12)
+  close(m.cdf_m2_conditioned, g[f"mass{i}_cdf"], 1e-11, 1e-300)
+  close(cb.mass.primary_mass_pdf_notnorm(m, g["m1"]), g[f"mass{i}_p1"], 1e-11)
+  close(cb.mass.p_m1m2(m, g["m1"], g["m2"]), g[f"mass{i}_p"], 1e-10)
+
+
+@pytest.mark.parametrize("i", range(len(RATE_CASES)))
+def test_rate_functions(cb, golden_models, i):
+  model, kw = RATE_CASES[i]
+  r = getattr(cb.rate, model)(**kw)
+  close(cb.rate.merger_rate(r, golden_models["zr"]), golden_models[f"rate{i}"], 1e-12)
+
+
+def build_like(cb, g, name, fp_mode="fp64", **over):
+  kind, kernel, binning, cmodel, hypers = LIKE_CASES[name]
+  pix = kind is not None
+  kw = dict(m1det=g["m1det"], m2det=g["m2det"], dL=g["dL"], pe_prior=g["pe_prior"])
+  gcat = None
+  if pix:
+    kw.update({k: g[k] for k in ("ra", "dec", "opt_nsides", "pixels_opt_nsides", "ra_pix", "dec_pix",
+                                 "gw_loc2d_pdf", "pixels_pe_opt_nside")})
+    gcat = cb.pixelated_catalog(cb.dVdz_completeness(g["z_range"]), p_cat=g["p_cat"], P_compl=g["P_compl"])
+  th = cb.theta_pe_det(**kw)
+  inj = cb.theta_inj_det(m1det=g["inj_m1det"], m2det=g["inj_m2det"], dL=g["inj_dL"], p_draw=g["inj_p_draw"])
+  sel = cb.selection_function(inj, float(g["N_inj"]), over.pop("N_eff", 5.))
+  cosmo = getattr(cb.cosmo, cmodel)(H0=70., Om0=0.25, z_max=5.)
+  pop = cb.population(cosmo, cb.mass.plp(), cb.rate.madau_dickinson(), gal_cat=gcat,
+                      **{k: over.pop(k) for k in ("R0", "Tobs", "scale_free") if k in over})
+  like = cb.hyperlikelihood(th, g["z_grids"], pop, sel, kind_p_gw3d=kind, kernel=kernel, binning=binning,
+                            num_bins=GOLDEN_NUM_BINS, pe_neff=2.0, cut_grid=2.0, fp_mode=fp_mode)
+  return like, pop, sel, hypers
+
+
+@pytest.mark.parametrize("name", list(LIKE_CASES))
+def test_likelihood_golden_fp64(cb, golden_like, golden_in1d, golden_inpix, name):
+  g = golden_inpix if LIKE_CASES[name][0] is not None else golden_in1d
+  like, pop, sel, hypers = build_like(cb, g, name)
+  for h, hl in enumerate(hypers):
+    lle, lnum, lnexp, lh = like.compute_all(**hl)
+    same_class(lle, golden_like[f"{name}_h{h}_lle"], RTOL64)
+    same_class([lnum, lnexp, lh], golden_like[f"{name}_h{h}_tot"], RTOL64)
+    close(like(**hl), golden_like[f"{name}_h{h}_tot"][2], RTOL64)
+    # p_gw arrays (valid pixels only: padded pixel rows are unspecified garbage in the reference)
+    ref = golden_like[f"{name}_h{h}_pgw"]
+    pl = pop.update(**hl)
+    got = like.p_gw3d(pl) if like.pixelated else like.p_gw1d(pl)
+    scale = np.nanmax(np.abs(ref))
+    if like.pixelated:
+      for e in range(ref.shape[0]):
+        n = int(g["neff_pixels"][e])
+        close(got[e, :n], ref[e, :n], 1e-8, 1e-11 * scale)
+    else:
+      close(got, ref, 1e-8, 1e-11 * scale)
+  close(sel.N_exp(pop.update(**hypers[0])), golden_like[f"{name}_h0_xi"], 1e-11)
+
+
+@pytest.mark.parametrize("name", list(LIKE_CASES))
+def test_likelihood_golden_batched(cb, golden_like, golden_in1d, golden_inpix, name):
+  """All hyper-points of a case in one batched call == the reference's one-at-a-time results."""
+  g = golden_inpix if LIKE_CASES[name][0] is not None else golden_in1d
+  like, pop, sel, hypers = build_like(cb, g, name)
+  keys = sorted({k for hl in hypers for k in hl})
+  defaults = {**pop.cosmo.as_dict, **pop.mass.as_dict, **pop.rate.as_dict}
+  batch = {k: np.array([hl.get(k, defaults[k]) for hl in hypers]) for k in keys}
+  lle, lnum, lnexp, lh = like.compute_all(**batch)
+  for h in range(len(hypers)):
+    same_class(lle[h], golden_like[f"{name}_h{h}_lle"], RTOL64)
+    same_class([lnum[h], lnexp[h], lh[h]], golden_like[f"{name}_h{h}_tot"], RTOL64)
+
+
+@pytest.mark.parametrize("name", ["1d_gauss_unbinned", "1d_epan_unbinned", "1d_epan_binned", "approx_gauss_unbinned",
+                                  "marg_unbinned", "marg_binned", "full_gauss"])
+def test_likelihood_golden_fp32(cb, golden_like, golden_in1d, golden_inpix, name):
+  g = golden_inpix if LIKE_CASES[name][0] is not None else golden_in1d
+  like, pop, sel, hypers = build_like(cb, g, name, fp_mode="fp32")
+  for h, hl in enumerate(hypers):
+    lle, lnum, lnexp, lh = like.compute_all(**hl)
+    same_class(lle, golden_like[f"{name}_h{h}_lle"], RTOL32)
+    same_class([lnum, lnexp, lh], golden_like[f"{name}_h{h}_tot"], RTOL32)
+    same_class(lle, golden_like[f"{name}_h{h}_lle"], RTOL32_TIGHT)
+
+
+def test_not_scale_free_and_neff_gate(cb, golden_like, golden_in1d):
+  like, pop, sel, _ = build_like(cb, golden_in1d, "1d_epan_binned", R0=17., Tobs=2.5, scale_free=False)
+  out = like.compute_all(H0=68., R0=21.)
+  close(out[1:], golden_like["notscalefree_tot"], RTOL64)
+  like, pop, sel, _ = build_like(cb, golden_in1d, "1d_epan_binned", N_eff=1e9)
+  out = np.asarray(like.compute_all(H0=68.)[1:], dtype=np.float64)
+  assert np.array_equal(out[1:], golden_like["neffgate_tot"][1:])      # log N_exp = -inf, log L = +inf
+
+
+def test_pe_neff_gate_gives_dbl_max(cb, golden_in1d):
+  """n_eff < pe_neff -> zero likelihood -> log 0 = -inf -> nan_to_num -> -DBL_MAX (likelihood.py:133-139,297)."""
+  g = golden_in1d
+  th = cb.theta_pe_det(m1det=g["m1det"], m2det=g["m2det"], dL=g["dL"], pe_prior=g["pe_prior"])
+  inj = cb.theta_inj_det(m1det=g["inj_m1det"], m2det=g["inj_m2det"], dL=g["inj_dL"], p_draw=g["inj_p_draw"])
+  pop = cb.population(cb.cosmo.flrw(z_max=5.), cb.mass.plp(), cb.rate.madau_dickinson())
+  like = cb.hyperlikelihood(th, g["z_grids"], pop, cb.selection_function(inj, float(g["N_inj"])), pe_neff=1e12)
+  lle, lnum, _, _ = like.compute_all(H0=70.)
+  assert np.all(lle == -np.finfo(np.float64).max)
+  assert lnum == -np.inf
+
+
+def test_constructor_errors(cb, golden_in1d, golden_inpix):
+  g = golden_inpix
+  th = cb.theta_pe_det(**{k: g[k] for k in ("m1det", "m2det", "dL", "pe_prior", "pixels_opt_nsides", "ra_pix",
+                                            "dec_pix", "gw_loc2d_pdf", "pixels_pe_opt_nside")})
+  gcat = cb.pixelated_catalog(cb.dVdz_completeness(g["z_range"]), p_cat=g["p_cat"], P_compl=g["P_compl"])
+  pop = cb.population(cb.cosmo.flrw(), cb.mass.plp(), cb.rate.madau_dickinson(), gal_cat=gcat)
+  with pytest.raises(AssertionError):
+    cb.hyperlikelihood(th, g["z_grids"], pop, None, kind_p_gw3d="bogus")
+  with pytest.raises(ValueError):
+    cb.hyperlikelihood(th, g["z_grids"], pop, None, kind_p_gw3d="approximate", bw_method="bogus")
+
+
+# ------------------------------------------------------------------------------------------
+# oracle parity on seeded synthetic inputs (larger than the fixtures, still seconds on the CPU)
+def _synthetic(nev, ns, nz, ninj, sky, seed):
+  from chimera_b200 import synth
+  ev = synth.make_events(nev, ns, seed=seed, sky=sky)
+  zg = synth.make_z_grids(ev["dL"], z_int_res=nz, H0_prior=(40., 120.))
+  inj, N_inj = synth.make_injections(ninj, seed=seed + 1)
+  cat = None
+  if sky:
+    ev = synth.pixelize(ev, nside_list=(64, 32, 16, 8), mean_npixels_event=8)
+    p_cat, P_compl = synth.smooth_p_cat(ev, zg, seed=seed + 2)
+    cat = dict(p_cat=p_cat, P_compl=P_compl, z_range=np.array([0.073, 1.3]))
+  return ev, zg, inj, N_inj, cat
+
+
+@pytest.mark.parametrize("kind,kernel,binning,fp_mode,rtol", [
+  (None, "gauss", False, "fp64", 1e-9), (None, "gauss", False, "fp32", 1e-3),
+  (None, "epan", True, "fp64", 1e-9), (None, "epan", True, "fp32", 1e-3),
+  ("approximate", "gauss", False, "fp64", 1e-9), ("approximate", "gauss", False, "fp32", 1e-3),
+  ("marginalized", "epan", True, "fp64", 1e-9), ("marginalized", "epan", False, "fp32", 1e-3),
+  ("full", "gauss", False, "fp64", 1e-9), ("full", "gauss", False, "fp32", 1e-3),
+])
+def test_oracle_parity_synthetic(cb, kind, kernel, binning, fp_mode, rtol):
+  from oracle import chimera_oracle as orc
+  sky = kind is not None
+  ev, zg, inj, N_inj, cat = _synthetic(24, 1500, 120, 20000, sky, seed=100 + (7 if sky else 0))
+  hypers = [dict(H0=55., Om0=0.2), dict(H0=70., Om0=0.25), dict(H0=90., Om0=0.35, alpha=3.1, gamma=2.2)]
+  kw = dict(m1det=ev["m1det"], m2det=ev["m2det"], dL=ev["dL"], pe_prior=ev["pe_prior"])
+  gcat = None
+  if sky:
+    kw.update({k: ev[k] for k in ("ra", "dec", "opt_nsides", "pixels_opt_nsides", "ra_pix", "dec_pix", "gw_loc2d_pdf",
+                                  "pixels_pe_opt_nside")})
+    gcat = cb.pixelated_catalog(cb.dVdz_completeness(cat["z_range"]), p_cat=cat["p_cat"], P_compl=cat["P_compl"])
+  th = cb.theta_pe_det(**kw)
+  sel = cb.selection_function(cb.theta_inj_det(**inj), N_inj, 5.)
+  pop = cb.population(cb.cosmo.flrw(z_max=5.), cb.mass.plp(), cb.rate.madau_dickinson(), gal_cat=gcat)
+  like = cb.hyperlikelihood(th, zg, pop, sel, kind_p_gw3d=kind, kernel=kernel, binning=binning, num_bins=200,
+                            fp_mode=fp_mode)
+  pop0 = orc.make_pop(orc.make_cosmo("flrw", z_max=5.), orc.make_mass("plp"), orc.make_rate("madau_dickinson"), catalog=cat)
+  opts = orc.make_opts(kind, kernel, None, 2.0, binning, 200, 2.0)
+  npx = ev.get("neff_pixels")
+  batch = {k: np.array([hl.get(k, dict(alpha=3.4, gamma=2.7)[k] if k in ("alpha", "gamma") else None) for hl in hypers])
+           for k in ("H0", "Om0", "alpha", "gamma")}
+  lle_b, lnum_b, lnexp_b, lh_b = like.compute_all(**batch)
+  for h, hl in enumerate(hypers):
+    ref = orc.compute_all(pop0, ev, zg, opts, inj, N_inj, 5., npx, **hl)
+    same_class(lle_b[h], ref[0], rtol)
+    same_class([lnum_b[h], lnexp_b[h], lh_b[h]], ref[1:], rtol)
+
+
+def test_selection_large_matches_oracle(cb):
+  from oracle import chimera_oracle as orc
+  from chimera_b200 import synth
+  inj, N_inj = synth.make_injections(300_000, seed=9)
+  sel = cb.selection_function(cb.theta_inj_det(**inj), N_inj, 5.)
+  pop = cb.population(cb.cosmo.mg_flrw(z_max=5.), cb.mass.bpl(), cb.rate.trunc_madau_dickinson(zmax=2.0))
+  H0 = np.linspace(50., 90., 5)
+  Xi0 = np.linspace(0.6, 1.8, 5)
+  got = sel.N_exp(pop.update(H0=H0, Xi0=Xi0, n=1.9))
+  pop0 = orc.make_pop(orc.make_cosmo("mg_flrw", z_max=5.), orc.make_mass("bpl"),
+                      orc.make_rate("trunc_madau_dickinson", zmax=2.0))
+  ref = [orc.N_exp(orc.pop_update(pop0, H0=h, Xi0=x, n=1.9), inj, N_inj, 5.)[0] for h, x in zip(H0, Xi0)]
+  close(got, ref, 1e-11)
+
+
+def test_compute_z_grids(cb, golden_setup):
+  g = golden_setup
+  th = cb.theta_pe_det(dL=g["dL"])
+  fid = cb.cosmo.flrw(H0=70., Om0=0.25, z_max=5.)
+  close(cb.compute_z_grids(fid, th, {"H0": [40., 120.]}, 40), g["zgrid_default"], 1e-11)
+  close(cb.compute_z_grids(fid, th, {"H0": [40., 120.], "Om0": [0.2, 0.4]}, 40, 3.), g["zgrid_sigma"], 1e-11)
+  close(cb.compute_z_grids(fid, th, None, 40, [1., 99.]), g["zgrid_pct"], 1e-11)
+  mg = cb.cosmo.mg_flrw(H0=70., Om0=0.25, z_max=5.)
+  close(cb.compute_z_grids(mg, th, {"H0": [50., 90.], "Xi0": [0.5, 2.], "n": [1., 3.]}, 40), g["zgrid_mg"], 1e-11)
