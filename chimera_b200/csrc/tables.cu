@@ -79,6 +79,8 @@ build_tables_kernel(ModelCfg mc, int n_hyper, const double* __restrict__ hyper, 
   for (int i = tid; i < rm; i += nt) {
     double y = (i == rm - 1) ? l1 : __dadd_rn(__dmul_rn((double)i, mstep), l0);
     double m = pow(10.0, y);
+    if (i == 0 && P[CHB_P_MGRID_FIRST] != 0.0) m = P[CHB_P_MGRID_FIRST];
+    if (i == rm - 1 && P[CHB_P_MGRID_LAST] != 0.0) m = P[CHB_P_MGRID_LAST];
     ms[i] = m;
     p2[i] = secondary_notnorm(mc.mass_model, P, m, P[CHB_P_MHIGH]);
     p1[i] = primary_notnorm(mc.mass_model, P, HC, m);

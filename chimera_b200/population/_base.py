@@ -85,6 +85,10 @@ def base_rows(n, cosmo=None, mass=None, rate=None, R0=1.0):
     if s is not None:
       fill_rows(rows, s)
   rows[:, _lib.SLOT["R0"]] = np.asarray(R0, dtype=np.float64)
+  # end knots of m_grid exactly as jnp.logspace(log10 m_low, log10 m_high, res) yields them
+  # (mass.py:46): whether they pass `m_low <= m <= m_high` depends on the last ulp.
+  rows[:, 26] = np.power(10., np.log10(rows[:, _lib.SLOT["m_low"]]))
+  rows[:, 27] = np.power(10., np.log10(rows[:, _lib.SLOT["m_high"]]))
   return rows
 
 

@@ -57,7 +57,11 @@ enum {
   CHB_P_MLOW = 9, CHB_P_MHIGH, CHB_P_ALPHA /* tpl/plp alpha, bpl alpha_1 */, CHB_P_BETA, CHB_P_DELTAM,
   CHB_P_ALPHA2, CHB_P_BREAKF, CHB_P_LAMBDAP, CHB_P_MUG, CHB_P_SIGMAG,                                 /* 9..18 */
   CHB_P_GAMMA = 21, CHB_P_KAPPA, CHB_P_ZP, CHB_P_RZMAX,                                               /* 21..24 */
-  CHB_P_R0 = 25
+  CHB_P_R0 = 25,
+  /* first / last knot of m_grid as the caller's libm evaluates 10**log10(m_low|m_high); the support
+   * tests `m_low <= m <= m_high` at those two knots (mass.py:240-245) sit on a rounding knife-edge,
+   * so they are taken verbatim when non-zero (0: computed on the device). */
+  CHB_P_MGRID_FIRST = 26, CHB_P_MGRID_LAST = 27
 };
 
 typedef struct {
