@@ -396,11 +396,6 @@ int chb_eval(chb_handle* h, int64_t n_hyper, const double* hyper, double* log_li
   CU(cudaMemcpyAsync(partials, h->partials.p, (size_t)n_hyper * 3 * sizeof(double), cudaMemcpyDeviceToHost, s), "D2H partials");
   if (d_pgw) CU(cudaMemcpyAsync(p_gw, d_pgw, pgw_n * sizeof(double), cudaMemcpyDeviceToHost, s), "D2H p_gw");
   CU(cudaStreamSynchronize(s), "eval synchronize");
-  for (int i = 0; i < 4; ++i) {
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]);
-    h->timings[i] = ms;
-  }
   return CHB_OK;
 }
 
@@ -515,7 +510,13 @@ int64_t chb_kernel_launch_count(const chb_handle* h) { return h ? h->launches : 
 
 int chb_last_timings(const chb_handle* h, double out[4]) {
   if (!h || !out) return CHB_ERR_INVALID;
-  for (int i = 0; i < 4; ++i) out[i] = h->timings[i];
+  cudaSetDevice(h->cfg.device);
+  if (cudaEventSynchronize(h->ev[4]) != cudaSuccess) { cudaGetLastError(); return CHB_ERR_STATE; }
+  for (int i = 0; i < 4; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]) != cudaSuccess) { cudaGetLastError(); return CHB_ERR_STATE; }
+    out[i] = ms;
+  }
   return CHB_OK;
 }
 

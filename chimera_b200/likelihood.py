@@ -29,7 +29,7 @@ def _bw_fields(bw_method):
 class hyperlikelihood(object):
   def __init__(self, theta_gw_det, z_grids, population, selection_function=None, kind_p_gw3d=None,
                kernel='epan', bw_method=None, cut_grid=2.0, binning=True, num_bins=200, pe_neff=2.0,
-               fp_mode='fp64', device=None, distributed=False, process_group=None):
+               fp_mode='fp64', device=None, distributed=False, process_group=None, presharded=False):
     self.theta_gw_det = theta_gw_det
     self.population = population
     self.z_grids = np.asarray(z_grids, dtype=np.float64)
@@ -64,11 +64,19 @@ class hyperlikelihood(object):
     bw_id, bw_val = _bw_fields(bw_method)
 
     # ---- sharding ---------------------------------------------------
+    # `presharded=True`: the arrays passed in are already this rank's shard (weak-scaling runs);
+    # otherwise every rank holds the global arrays and keeps its contiguous chunk.
     self.rank, self.world = parallel.dist_info(process_group) if distributed else (0, 1)
     self.group = process_group
-    self._ev_counts = [parallel.shard_bounds(self.nevents, r, self.world) for r in range(self.world)]
-    self._ev_counts = [hi - lo for lo, hi in self._ev_counts]
-    lo, hi = parallel.shard_bounds(self.nevents, self.rank, self.world)
+    self.presharded = bool(presharded) and self.world > 1
+    if self.presharded:
+      self._ev_counts = parallel.allgather_counts(self.nevents, process_group)
+      lo, hi = 0, self.nevents
+      self.nevents = int(sum(self._ev_counts))
+    else:
+      self._ev_counts = [parallel.shard_bounds(self.nevents, r, self.world) for r in range(self.world)]
+      self._ev_counts = [b - a for a, b in self._ev_counts]
+      lo, hi = parallel.shard_bounds(self.nevents, self.rank, self.world)
     self._ev_slice = slice(lo, hi)
     if device is None:
       device = 0
@@ -106,7 +114,7 @@ class hyperlikelihood(object):
     if sel is not None:
       ti = sel.theta_inj_det
       arrs = [np.ravel(np.asarray(x, dtype=np.float64)) for x in (ti.m1det, ti.m2det, ti.dL, ti.p_draw)]
-      ilo, ihi = parallel.shard_bounds(arrs[0].size, self.rank, self.world)
+      ilo, ihi = (0, arrs[0].size) if self.presharded else parallel.shard_bounds(arrs[0].size, self.rank, self.world)
       if ihi > ilo:
         self.engine.set_injections(*[a[ilo:ihi] for a in arrs])
 
@@ -122,6 +130,16 @@ class hyperlikelihood(object):
         lle = parallel.allgather_events(lle, self._ev_counts, self.group)
     fin = self.engine.finalize(rows, part, self.nevents)
     return rows, batched, lle, part, pgw, fin
+
+  def partials_device(self, d_rows, d_partials, stream=None):
+    """Device-resident entry (torch f64 CUDA tensors): rows (n, CHB_NPAR) -> partials (n, 3), summed
+    over ranks with one NCCL all-reduce when distributed.  Asynchronous on torch's current stream."""
+    import torch
+    st = torch.cuda.current_stream().cuda_stream if stream is None else stream
+    self.engine.eval_device(d_rows, d_partials, None, st)
+    if self.world > 1:
+      parallel.allreduce_partials(d_partials, self.group)
+    return d_partials
 
   @staticmethod
   def _shape(x, batched):

@@ -26,6 +26,20 @@ def dist_info(group=None):
   return dist.get_rank(group), dist.get_world_size(group)
 
 
+def allgather_counts(n_local, group=None):
+  """Per-rank item counts (list of ints) for pre-sharded inputs."""
+  import torch
+  import torch.distributed as dist
+  if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+    return [int(n_local)]
+  t = torch.tensor([int(n_local)], dtype=torch.int64)
+  if dist.get_backend(group) == "nccl":
+    t = t.cuda()
+  outs = [torch.empty_like(t) for _ in range(dist.get_world_size(group))]
+  dist.all_gather(outs, t, group=group)
+  return [int(o.item()) for o in outs]
+
+
 def allreduce_partials(partials, group=None):
   """SUM all-reduce of the partials over ranks.  Accepts a NumPy array (moved through a CPU
   tensor: gloo, or NCCL via a staging copy to the current CUDA device) or a torch tensor that

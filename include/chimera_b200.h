@@ -188,6 +188,10 @@ int64_t chb_kernel_launch_count(const chb_handle* h);
  * out[0]=tables, out[1]=numerator (reweight+KDE+z-integral), out[2]=selection, out[3]=reduce */
 int chb_last_timings(const chb_handle* h, double out[4]);
 
+/* Measured MUFU.EX2 throughput [exp/s] of `device` (micro-benchmark run for ~`seconds`): the
+ * denominator of the KDE roofline fraction. */
+int chb_mufu_peak(int device, double seconds, double* exp_per_s);
+
 #ifdef __cplusplus
 }
 #endif

