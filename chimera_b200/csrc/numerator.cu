@@ -27,7 +27,7 @@ int numerator_block_threads() { return NUM_THREADS; }
 
 // shared-memory plan (offsets in doubles), identical on host and device
 struct SmemPlan {
-  int tab, zgrid, tw, dV, rj, jac, pgw, eg, dens, bc, bs, red, stage, total;
+  int tab, zgrid, tw, dV, rj, jac, pgw, eg, dens, bc, bs, xwb, part, red, stage, total;
 };
 __host__ __device__ inline SmemPlan make_plan(int tab_total, int Nz, int B, int Ns, int kind, bool stage_in_smem) {
   SmemPlan p;
@@ -43,6 +43,8 @@ __host__ __device__ inline SmemPlan make_plan(int tab_total, int Nz, int B, int 
   p.dens = o; o += Nz;
   p.bc = o; o += B;
   p.bs = o; o += B;
+  p.xwb = o; o += B;                                   // float2 per bin (fp32 mode)
+  p.part = o; o += (NUM_WARPS * Nz + 1) / 2;            // float [NUM_WARPS][Nz] cross-warp partials
   p.red = o; o += 64;
   o = (o + 1) & ~1;
   p.stage = o;
@@ -86,52 +88,113 @@ __device__ __forceinline__ void kde1d_f64(const double* __restrict__ x, const do
   (void)inv_bw;
 }
 
-// fp32 pair sums: data (x', w) as float2 in shared memory, x' = (x - c) * s pre-scaled so that the
+// fp32 pair sums: data (x', w') as float2 in shared memory, x' = (x - c) * s pre-scaled so that the
 // Gaussian is 2^-(g'-x')^2 (s = sqrt(log2(e)/2)/bw) and the Epanechnikov support is |g'-x'|<=1
-// (s = 1/bw).  Every lane keeps R grid points in registers; all lanes read the same sample
-// (shared-memory broadcast); each warp takes a slice of the samples; partial sums are combined
-// across warps in fp64.
+// (s = 1/bw); centring and scaling happen in fp64 before the cast.  Every lane keeps R grid points
+// in registers; all lanes of a warp read the same sample (one broadcast LDS.64 per R pairs); the 16
+// warps split the samples; per-warp partial sums are combined in fp64.  Per pair the Gaussian costs
+// FADD + FMUL + MUFU.EX2 + FFMA: the loop is bound by the MUFU pipe (16 ex2/clk/SM).
+// 2^x on the MUFU pipe, flush-to-zero: no range fix-up code around the instruction (exp2f() adds an
+// FSETP and two predicated FMULs per call to keep denormal results, which are irrelevant here).
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <int R>
-__device__ __forceinline__ void kde1d_f32_tile(const float2* __restrict__ xw, int n, const double* __restrict__ eg,
+__device__ __forceinline__ void kde1d_f32_pass(const float2* __restrict__ xw, int n, const double* __restrict__ eg,
                                                int G, int g_base, double c, double s, int kernel,
-                                               double* __restrict__ part /* [NUM_WARPS][G] */) {
+                                               float* __restrict__ part /* [NUM_WARPS][G] */) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float gp[R], acc[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     int g = g_base + r * 32 + lane;
-    gp[r] = (g < G) ? (float)((eg[g] - c) * s) : 1e30f;
+    gp[r] = (g < G) ? (float)((eg[g] - c) * s) : 3.0e18f;   // far away: contributes exactly 0
     acc[r] = 0.f;
   }
   const int per = (n + NUM_WARPS - 1) / NUM_WARPS;
-  const int j0 = warp * per, j1 = min(n, j0 + per);
+  const int j0 = min(n, warp * per), j1 = min(n, j0 + per);
   if (kernel == CHB_KERNEL_GAUSS) {
-#pragma unroll 2
+#pragma unroll 4
     for (int j = j0; j < j1; ++j) {
       const float2 v = xw[j];
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        float d = gp[r] - v.x;
-        acc[r] = fmaf(v.y, exp2f(-d * d), acc[r]);
+        const float d = gp[r] - v.x;
+        acc[r] = fmaf(v.y, ex2_ftz(-(d * d)), acc[r]);
       }
     }
   } else {
-#pragma unroll 2
+#pragma unroll 4
     for (int j = j0; j < j1; ++j) {
       const float2 v = xw[j];
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        float d = gp[r] - v.x;
-        float k = fmaxf(1.f - d * d, 0.f);
-        acc[r] = fmaf(v.y, k, acc[r]);
+        const float d = gp[r] - v.x;
+        acc[r] = fmaf(v.y, fmaxf(fmaf(-d, d, 1.f), 0.f), acc[r]);
       }
     }
   }
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     int g = g_base + r * 32 + lane;
-    if (g < G) part[warp * G + g] = (double)acc[r];
+    if (g < G) part[warp * G + g] = acc[r];
   }
+}
+
+// dens[g] = scale * sum_j w'_j K(g' - x'_j).  Must be called by the whole CTA.
+__device__ __forceinline__ void kde1d_f32(const float2* __restrict__ xw, int n, const double* __restrict__ eg, int G,
+                                          double c, double s, int kernel, double scale, float* __restrict__ part,
+                                          double* __restrict__ dens) {
+  // register tile height: fewest (passes x R), larger R on ties
+  int R = 1, best = 1 << 30;
+  for (int r = 8; r >= 1; --r) {
+    int cost = ((G + 32 * r - 1) / (32 * r)) * r;
+    if (cost < best) { best = cost; R = r; }
+  }
+  for (int gb = 0; gb < G; gb += 32 * R) {
+    switch (R) {
+      case 1: kde1d_f32_pass<1>(xw, n, eg, G, gb, c, s, kernel, part); break;
+      case 2: kde1d_f32_pass<2>(xw, n, eg, G, gb, c, s, kernel, part); break;
+      case 3: kde1d_f32_pass<3>(xw, n, eg, G, gb, c, s, kernel, part); break;
+      case 4: kde1d_f32_pass<4>(xw, n, eg, G, gb, c, s, kernel, part); break;
+      case 5: kde1d_f32_pass<5>(xw, n, eg, G, gb, c, s, kernel, part); break;
+      case 6: kde1d_f32_pass<6>(xw, n, eg, G, gb, c, s, kernel, part); break;
+      case 7: kde1d_f32_pass<7>(xw, n, eg, G, gb, c, s, kernel, part); break;
+      default: kde1d_f32_pass<8>(xw, n, eg, G, gb, c, s, kernel, part); break;
+    }
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < G; g += NUM_THREADS) {
+    double acc = 0.0;
+#pragma unroll
+    for (int w = 0; w < NUM_WARPS; ++w) acc += (double)part[w * G + g];
+    dens[g] = acc * scale;
+  }
+}
+
+// One entry for both arithmetic modes.  x/w: fp64 data set (n entries); in fp32 mode it is converted
+// into `xw` (which may alias x: element j of xw overlays element j of x) and the pair sums run in
+// fp32.  dens[g] = scale_pdf * sum_j (w_j/W) K((eg[g]-x_j)/bw) / bw, K including its normalisation.
+__device__ __forceinline__ void kde1d_any(int fp_mode, double* x, const double* w, int n, float2* xw,
+                                          const double* __restrict__ eg, int G, double bw, double W, int kernel,
+                                          double scale_pdf, float* part, double* dens) {
+  if (fp_mode == CHB_FP64) {
+    kde1d_f64(x, w, n, eg, G, bw, kernel, scale_pdf / (W * bw), dens);
+    return;
+  }
+  const double c = 0.5 * (eg[0] + eg[G - 1]);
+  const double s = (kernel == CHB_KERNEL_GAUSS) ? 0.8493218002880191 / bw : 1.0 / bw;   // sqrt(log2(e)/2)
+  const double knorm = (kernel == CHB_KERNEL_GAUSS) ? 0.3989422804014327 : 0.75;
+  const double invW = 1.0 / W;
+  for (int j = threadIdx.x; j < n; j += NUM_THREADS) {
+    const double xv = x[j], wv = w[j];
+    xw[j] = make_float2((float)((xv - c) * s), (float)(wv * invW));
+  }
+  __syncthreads();
+  kde1d_f32(xw, n, eg, G, c, s, kernel, scale_pdf * knorm / bw, part, dens);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -142,17 +205,18 @@ __device__ __forceinline__ double nan_to_num_log(double like) {
   return l;
 }
 
+template <bool STAGE_SMEM>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 numerator_kernel(const NumArgs a) {
   extern __shared__ __align__(16) double sm[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ double P[CHB_NPAR];
   __shared__ double HC[CHB_NHC];
-  __shared__ double L[8];   // full-3D whitening: L00 L10 L11 L20 L21 L22, log_norm
+  __shared__ double L[8];   // full-3D whitening: L00 L10 L11 L20 L21 L22, log_norm, #masked grid points
 
   const TableLayout lay = a.mc.lay;
   const int Ns = a.Ns, Nz = a.Nz, Pp = a.P, B = a.binning ? a.num_bins : 0;
-  const bool in_smem = (a.scratch_stride == 0);
+  constexpr bool in_smem = STAGE_SMEM;
   const SmemPlan pl = make_plan(lay.total(), Nz, B, Ns, a.kind, in_smem);
   double* tab = sm + pl.tab;
   double* zgrid = sm + pl.zgrid;
@@ -165,8 +229,11 @@ numerator_kernel(const NumArgs a) {
   double* dens = sm + pl.dens;
   double* bc = sm + pl.bc;
   double* bs = sm + pl.bs;
+  float2* xwb = reinterpret_cast<float2*>(sm + pl.xwb);
+  float* part = reinterpret_cast<float*>(sm + pl.part);
   double* red = sm + pl.red;
-  double* stage = in_smem ? (sm + pl.stage) : (a.scratch + (size_t)blockIdx.x * a.scratch_stride);
+  double* stage;
+  if constexpr (STAGE_SMEM) stage = sm + pl.stage; else stage = a.scratch + (size_t)blockIdx.x * a.scratch_stride;
   double* zs = stage;
   double* ws = stage + Ns;
   double* y1 = stage + 2 * Ns;   // full only
@@ -309,7 +376,8 @@ numerator_kernel(const NumArgs a) {
       if (a.bw_method == CHB_BW_SCOTT) bw = pow(neff_k, -0.2) * dstd;
       else if (a.bw_method == CHB_BW_SILVERMAN) bw = pow(neff_k * 3.0 / 4.0, -0.2) * dstd;
       else bw = a.bw_value * dstd;
-      kde1d_f64(dx, dw, dn, eg, G, bw, a.kernel, norm / (W * bw), dens);
+      kde1d_any(a.fp_mode, const_cast<double*>(dx), dw, dn, a.binning ? xwb : reinterpret_cast<float2*>(zs), eg, G, bw, W,
+                a.kernel, norm, part, dens);
       __syncthreads();
       for (int k = tid; k < Nz; k += NUM_THREADS) pgw[k] = interp_lr(zgrid[k], eg, dens, G, 0.0, 0.0);
       __syncthreads();
@@ -383,8 +451,9 @@ numerator_kernel(const NumArgs a) {
         else if (a.bw_method == CHB_BW_SILVERMAN) bw = pow(neff_k * 3.0 / 4.0, -0.2) * dstd;
         else bw = a.bw_value * dstd;
         // W == 0 (no weight in the pixel) -> w/W = NaN for every sample in the reference
-        const double scale = (W != 0.0) ? (norm * gwp[p]) / (W * bw) : nan("");
-        kde1d_f64(dx, dw, dn, eg, G, bw, CHB_KERNEL_EPAN, 1.0, dens);
+        const double scale = (W != 0.0) ? (norm * gwp[p]) : nan("");
+        kde1d_any(a.fp_mode, const_cast<double*>(dx), dw, dn, a.binning ? xwb : reinterpret_cast<float2*>(zs + o0), eg, G, bw, W,
+                  CHB_KERNEL_EPAN, 1.0, part, dens);
         __syncthreads();
         for (int k = tid; k < Nz; k += NUM_THREADS) {
           const double raw = interp_lr(zgrid[k], eg, dens, G, 0.0, 0.0);
@@ -440,37 +509,98 @@ numerator_kernel(const NumArgs a) {
       __syncthreads();
       const double l00 = L[0], l10 = L[1], l11 = L[2], l20 = L[3], l21 = L[4], l22 = L[5], lognorm = L[6];
       // whiten samples about the weighted mean: y = (x - mu)^T L ; weights normalised in place
+      const bool f32 = (a.fp_mode == CHB_FP32);
+      float4* yw = reinterpret_cast<float4*>(y1);      // fp32 mode: (y0,y1,y2,w') per sample over the y1|y2 region
+      const double ps = 0.8493218002880191;            // sqrt(log2(e)/2): exp(-d^2/2) = 2^-(ps d)^2
       for (int j = tid; j < Ns; j += NUM_THREADS) {
         const double r0 = zs[j] - m0, r1 = ra[j] - m1, r2 = dec[j] - m2;
-        zs[j] = r0 * l00 + r1 * l10 + r2 * l20;
-        y1[j] = r1 * l11 + r2 * l21;
-        y2[j] = r2 * l22;
-        ws[j] = ws[j] / W;
+        const double w0 = r0 * l00 + r1 * l10 + r2 * l20, w1 = r1 * l11 + r2 * l21, w2 = r2 * l22;
+        const double wn = ws[j] / W;
+        if (f32) {
+          yw[j] = make_float4((float)(w0 * ps), (float)(w1 * ps), (float)(w2 * ps), (float)wn);
+        } else {
+          zs[j] = w0; y1[j] = w1; y2[j] = w2; ws[j] = wn;
+        }
       }
       if (pout) for (int i = tid; i < Pp * Nz; i += NUM_THREADS) pout[i] = 0.0;
-      __syncthreads();
       const double zlo = zmn - a.cut_grid * zstd, zhi = zmx + a.cut_grid * zstd;   // likelihood.py:225
+      // compact list of the grid points inside the cut window
+      int* kmask = reinterpret_cast<int*>(dens);
+      if (tid == 0) {
+        int c = 0;
+        for (int k = 0; k < Nz; ++k) if (zgrid[k] <= zhi && zgrid[k] >= zlo) kmask[c++] = k;
+        L[7] = (double)c;
+      }
+      __syncthreads();
+      const int nmask = (int)L[7];
       const double* rap = a.ra_pix + (size_t)ev * Pp;
       const double* dep = a.dec_pix + (size_t)ev * Pp;
-      for (int i = warp; i < npix * Nz; i += NUM_WARPS) {
-        const int p = i / Nz, k = i - p * Nz;
-        const double z = zgrid[k];
-        if (!(z <= zhi && z >= zlo)) continue;
-        const double r0 = z - m0, r1 = rap[p] - m1, r2 = dep[p] - m2;
-        const double q0 = r0 * l00 + r1 * l10 + r2 * l20, q1 = r1 * l11 + r2 * l21, q2 = r2 * l22;
-        double acc = 0.0;
-        for (int j = lane; j < Ns; j += 32) {
-          const double d0 = zs[j] - q0, d1 = y1[j] - q1, d2 = y2[j] - q2;
-          acc += ws[j] * exp(lognorm - 0.5 * (d0 * d0 + d1 * d1 + d2 * d2));
+      const int npts = npix * nmask;
+      if (!f32) {
+        for (int i = warp; i < npts; i += NUM_WARPS) {
+          const int p = i / nmask, k = kmask[i - p * nmask];
+          const double r0 = zgrid[k] - m0, r1 = rap[p] - m1, r2 = dep[p] - m2;
+          const double q0 = r0 * l00 + r1 * l10 + r2 * l20, q1 = r1 * l11 + r2 * l21, q2 = r2 * l22;
+          double acc = 0.0;
+          for (int j = lane; j < Ns; j += 32) {
+            const double d0 = zs[j] - q0, d1 = y1[j] - q1, d2 = y2[j] - q2;
+            acc += ws[j] * exp(lognorm - 0.5 * (d0 * d0 + d1 * d1 + d2 * d2));
+          }
+          acc = warp_sum(acc);
+          if (lane == 0) {
+            const double v = acc * norm;
+            if (pout) pout[(size_t)p * Nz + k] = v;
+            const double pc = has_cat ? pcat_ev[(size_t)p * Nz + k] : 0.0;
+            if (pc != -100.0) {
+              const double pgal = has_cat ? fR * pc + (1.0 - pcompl_ev[k]) * dV[k] : dV[k];
+              like_acc += (v * (pgal * rj[k]) / jac[k]) * tw[k];
+            }
+          }
         }
-        acc = warp_sum(acc);
-        if (lane == 0) {
-          const double v = acc * norm;
-          if (pout) pout[(size_t)p * Nz + k] = v;
-          const double pc = has_cat ? pcat_ev[(size_t)p * Nz + k] : 0.0;
-          if (pc != -100.0) {
-            const double pgal = has_cat ? fR * pc + (1.0 - pcompl_ev[k]) * dV[k] : dV[k];
-            like_acc += (v * (pgal * rj[k]) / jac[k]) * tw[k];
+      } else {
+        // fp32: every lane owns FR evaluation points, the warp streams all samples (broadcast LDS.128);
+        // per pair 3 FADD + FMUL + 2 FFMA + MUFU.EX2 + FFMA.
+        constexpr int FR = 2;
+        const double enorm = exp(lognorm) * norm;
+        const int ntiles = (npts + 32 * FR - 1) / (32 * FR);
+        for (int t = warp; t < ntiles; t += NUM_WARPS) {
+          float q0[FR], q1[FR], q2[FR], acc[FR];
+          int pk[FR];
+#pragma unroll
+          for (int r = 0; r < FR; ++r) {
+            const int i = t * 32 * FR + r * 32 + lane;
+            pk[r] = -1; acc[r] = 0.f;
+            q0[r] = q1[r] = q2[r] = 1.0e18f;
+            if (i < npts) {
+              const int p = i / nmask, k = kmask[i - p * nmask];
+              pk[r] = p * Nz + k;
+              const double r0 = zgrid[k] - m0, r1 = rap[p] - m1, r2 = dep[p] - m2;
+              q0[r] = (float)((r0 * l00 + r1 * l10 + r2 * l20) * ps);
+              q1[r] = (float)((r1 * l11 + r2 * l21) * ps);
+              q2[r] = (float)((r2 * l22) * ps);
+            }
+          }
+#pragma unroll 4
+          for (int j = 0; j < Ns; ++j) {
+            const float4 v = yw[j];
+#pragma unroll
+            for (int r = 0; r < FR; ++r) {
+              const float d0 = v.x - q0[r], d1 = v.y - q1[r], d2 = v.z - q2[r];
+              const float e = fmaf(d2, d2, fmaf(d1, d1, d0 * d0));
+              acc[r] = fmaf(v.w, ex2_ftz(-e), acc[r]);
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < FR; ++r) {
+            if (pk[r] < 0) continue;
+            const int p = pk[r] / Nz, k = pk[r] - p * Nz;
+            const double v = (double)acc[r] * enorm;
+            if (pout) pout[(size_t)p * Nz + k] = v;
+            const double pc = has_cat ? pcat_ev[(size_t)p * Nz + k] : 0.0;
+            if (pc != -100.0) {
+              const double pgal = has_cat ? fR * pc + (1.0 - pcompl_ev[k]) * dV[k] : dV[k];
+              like_acc += (v * (pgal * rj[k]) / jac[k]) * tw[k];
+            }
           }
         }
       }
@@ -482,9 +612,12 @@ numerator_kernel(const NumArgs a) {
 }
 
 cudaError_t numerator_configure(size_t smem) {
-  return cudaFuncSetAttribute(numerator_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(numerator_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(numerator_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 cudaError_t launch_numerator(const NumArgs& a, int grid, int block, size_t smem, cudaStream_t s) {
-  numerator_kernel<<<grid, block, smem, s>>>(a);
+  if (a.scratch_stride == 0) numerator_kernel<true><<<grid, block, smem, s>>>(a);
+  else numerator_kernel<false><<<grid, block, smem, s>>>(a);
   return cudaGetLastError();
 }

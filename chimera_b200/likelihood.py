@@ -136,6 +136,7 @@ class hyperlikelihood(object):
     over ranks with one NCCL all-reduce when distributed.  Asynchronous on torch's current stream."""
     import torch
     st = torch.cuda.current_stream().cuda_stream if stream is None else stream
+    st = st or 1      # 0 is the legacy default stream: name it explicitly (cudaStreamLegacy), NULL means 'handle stream'
     self.engine.eval_device(d_rows, d_partials, None, st)
     if self.world > 1:
       parallel.allreduce_partials(d_partials, self.group)
