@@ -65,6 +65,7 @@ EXPORTS = {
   "chb_model_tables": (C.c_int, [C.POINTER(chb_config), _dp, _dp, _dp, _dp, _dp, _dp]),
   "chb_kernel_launch_count": (C.c_int64, [_hp]),
   "chb_last_timings": (C.c_int, [_hp, _dp]),
+  "chb_phase_profile": (C.c_int, [_hp, C.c_int, _dp]),
   "chb_mufu_peak": (C.c_int, [C.c_int, C.c_double, _dp]),
 }
 

@@ -55,6 +55,12 @@ struct chb_handle {
   std::vector<double> h_ra_pix;
   DevBuf<double> m1d, m2d, dL, prior, ra, dec, zgrids, ra_pix, dec_pix, gw_pdf, p_cat, P_compl;
   DevBuf<int> pix_off, neff_pix;
+  DevBuf<unsigned long long> prof;
+  DevBuf<float4> s4;
+  DevBuf<float2> l2;
+  DevBuf<double> catA, catB;
+  bool cat_collapsed = false;
+  bool want_prof = false;
   DevBuf<double> inj_m1, inj_m2, inj_dL, inj_pd;
   // per-eval buffers
   DevBuf<double> hyper, tabs, HC, log_like, like_raw, tile_part, partials, pgw, scratch;
@@ -146,6 +152,8 @@ void chb_destroy(chb_handle* h) {
                            &h->hyper, &h->tabs, &h->HC, &h->log_like, &h->like_raw, &h->tile_part, &h->partials, &h->pgw, &h->scratch};
   for (auto* b : dbl) b->release();
   h->pix_off.release();
+  h->prof.release();
+  h->s4.release(); h->l2.release(); h->catA.release(); h->catB.release();
   h->neff_pix.release();
   for (auto& evn : h->ev) if (evn) cudaEventDestroy(evn);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -211,6 +219,7 @@ int chb_set_catalog(chb_handle* h, const double* p_cat, const double* P_compl) {
   CU(h->p_cat.upload(p_cat, (size_t)h->Nev * h->P * h->Nz), "upload p_cat");
   CU(h->P_compl.upload(P_compl, (size_t)h->Nev * h->Nz), "upload P_compl");
   h->have_catalog = true;
+  h->cat_collapsed = false;
   return CHB_OK;
 }
 
@@ -273,7 +282,25 @@ static int prepare(chb_handle* h) {
     CU(h->dL.upload(h->h_dL.data(), n), "upload dL"); CU(h->prior.upload(h->h_prior.data(), n), "upload pe_prior");
     if (!h->h_ra.empty()) { CU(h->ra.upload(h->h_ra.data(), n), "upload ra"); CU(h->dec.upload(h->h_dec.data(), n), "upload dec"); }
   }
+  if (h->cfg.fp_mode == CHB_FP32) {
+    // single-precision copies for the fp32 reweighting path (device order = the order just uploaded)
+    std::vector<double> m1(n), m2(n), dl(n), pr(n);
+    CU(cudaMemcpy(m1.data(), h->m1d.p, n * sizeof(double), cudaMemcpyDeviceToHost), "D2H m1det");
+    CU(cudaMemcpy(m2.data(), h->m2d.p, n * sizeof(double), cudaMemcpyDeviceToHost), "D2H m2det");
+    CU(cudaMemcpy(dl.data(), h->dL.p, n * sizeof(double), cudaMemcpyDeviceToHost), "D2H dL");
+    CU(cudaMemcpy(pr.data(), h->prior.p, n * sizeof(double), cudaMemcpyDeviceToHost), "D2H pe_prior");
+    std::vector<float4> s4(n);
+    std::vector<float2> l2(n);
+    for (size_t i = 0; i < n; ++i) {
+      s4[i] = make_float4((float)dl[i], (float)m1[i], (float)m2[i], (float)(1.0 / pr[i]));
+      l2[i] = make_float2((float)std::log2(m1[i]), (float)std::log2(m2[i]));
+    }
+    CU(h->s4.upload(s4.data(), n), "upload packed samples");
+    CU(h->l2.upload(l2.data(), n), "upload log2 masses");
+    h->m1d.release(); h->m2d.release(); h->dL.release(); h->prior.release();   // fp64 copies are not read in this mode
+  }
   h->dirty = false;
+  h->cat_collapsed = false;
   return CHB_OK;
 }
 
@@ -311,6 +338,19 @@ static int eval_impl(chb_handle* h, int64_t n_hyper, const double* d_hyper, doub
     a.zgrids = h->zgrids.p; a.pix_off = h->pix_off.p; a.ra_pix = h->ra_pix.p; a.dec_pix = h->dec_pix.p;
     a.gw_pdf = h->gw_pdf.p; a.neff_pix = h->neff_pix.p;
     a.p_cat = h->have_catalog ? h->p_cat.p : nullptr; a.P_compl = h->have_catalog ? h->P_compl.p : nullptr;
+    a.s4 = h->s4.p; a.l2 = h->l2.p;
+    a.catA = nullptr; a.catB = nullptr;
+    if (c.kind_p_gw == CHB_PGW_APPROX && h->have_catalog) {
+      if (!h->cat_collapsed) {
+        CU(h->catA.alloc((size_t)h->Nev * h->Nz), "alloc catA");
+        CU(h->catB.alloc((size_t)h->Nev * h->Nz), "alloc catB");
+        CU(launch_catalog_collapse((int)h->Nev, (int)h->P, (int)h->Nz, h->p_cat.p, h->gw_pdf.p, h->neff_pix.p,
+                                   h->catA.p, h->catB.p, s), "catalog_collapse launch");
+        h->launches++;
+        h->cat_collapsed = true;
+      }
+      a.catA = h->catA.p; a.catB = h->catB.p;
+    }
     if (!h->have_catalog) a.mc.catalog_kind = 0;
     a.n_hyper = (int)n_hyper; a.hyper = d_hyper; a.tabs = h->tabs.p; a.HC = h->HC.p;
     CU(h->like_raw.alloc((size_t)n_hyper * h->Nev), "alloc like_raw");
@@ -331,6 +371,8 @@ static int eval_impl(chb_handle* h, int64_t n_hyper, const double* d_hyper, doub
       a.scratch = h->scratch.p;
     }
     h->num_grid = grid; h->num_smem = smem;
+    a.prof = nullptr;
+    if (h->want_prof) { CU(h->prof.alloc((size_t)grid * 8), "alloc profile"); a.prof = h->prof.p; }
     CU(launch_numerator(a, grid, numerator_block_threads(), smem, s), "numerator launch");
     h->launches++;
   }
@@ -504,6 +546,23 @@ int chb_model_tables(const chb_config* cfg, const double* params, double* z_grid
   }
   dP.release(); dT.release(); dHC.release();
   return rc;
+}
+
+int chb_phase_profile(chb_handle* h, int enable, double out[8]) {
+  if (!h) return CHB_ERR_INVALID;
+  cudaSetDevice(h->cfg.device);
+  if (out) {
+    for (int i = 0; i < 8; ++i) out[i] = 0.0;
+    if (h->want_prof && h->prof.p && h->num_grid > 0) {
+      std::vector<unsigned long long> v((size_t)h->num_grid * 8);
+      CU(cudaStreamSynchronize(h->stream), "synchronize");
+      CU(cudaDeviceSynchronize(), "synchronize");
+      CU(cudaMemcpy(v.data(), h->prof.p, v.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost), "D2H profile");
+      for (int b = 0; b < h->num_grid; ++b) for (int i = 0; i < 8; ++i) out[i] += (double)v[(size_t)b * 8 + i] / h->num_grid;
+    }
+  }
+  h->want_prof = enable != 0;
+  return CHB_OK;
 }
 
 int64_t chb_kernel_launch_count(const chb_handle* h) { return h ? h->launches : 0; }

@@ -18,12 +18,19 @@ struct NumArgs {
   // event data, samples permuted so that each pixel's samples are contiguous
   int Nev, Ns, Nz, P;
   const double *m1d, *m2d, *dL, *prior, *ra, *dec;   // (Nev, Ns)
+  // fp32 mode: packed single-precision copies {dL, m1det, m2det, 1/pe_prior} and {log2 m1det, log2 m2det}
+  const float4* s4;
+  const float2* l2;
   const double* zgrids;                              // (Nev, Nz)
   const int* pix_off;                                // (Nev, P+2) sample offsets per pixel slot
   const double *ra_pix, *dec_pix, *gw_pdf;           // (Nev, P)
   const int* neff_pix;                               // (Nev,)
   const double* p_cat;                               // (Nev, P, Nz)
   const double* P_compl;                             // (Nev, Nz)
+  // 'approximate' kind: hyper-independent pixel sums A[ev,k] = sum_p gw_pdf[p] p_cat[p,k] and
+  // B[ev,k] = sum_p gw_pdf[p] [p_cat[p,k] != -100] over the event's valid pixels (catalog_collapse_kernel)
+  const double* catA;
+  const double* catB;
   // hyper-points
   int n_hyper;
   const double* hyper;   // (n_hyper, CHB_NPAR)
@@ -33,6 +40,8 @@ struct NumArgs {
   double* log_like;      // (n_hyper, Nev)
   double* like_raw;      // (n_hyper, Nev) integral before log / nan_to_num
   double* p_gw_out;      // optional (n_hyper, Nev, [P,] Nz)
+  // optional phase profile: (gridDim, 8) SM-clock cycles accumulated by thread 0 of every CTA
+  unsigned long long* prof;
   // per-CTA global scratch for sample staging when it does not fit in shared memory
   double* scratch;
   long long scratch_stride;   // doubles per CTA (0: staging lives in shared memory)
@@ -55,6 +64,8 @@ size_t numerator_smem_bytes(const NumArgs& a, bool stage_in_smem);
 long long numerator_scratch_doubles(const NumArgs& a);
 int numerator_block_threads();
 cudaError_t numerator_configure(size_t smem);
+cudaError_t launch_catalog_collapse(int Nev, int P, int Nz, const double* p_cat, const double* gw_pdf, const int* neff_pix,
+                                   double* catA, double* catB, cudaStream_t s);
 cudaError_t launch_reduce(int n_hyper, int Nev, int tiles, const double* d_log_like, const double* d_tile_part,
                           double* d_partials, cudaStream_t s);
 cudaError_t launch_model_eval(const ModelCfg& mc, int which, const double* d_params, const double* d_tabs,

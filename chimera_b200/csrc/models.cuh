@@ -25,8 +25,17 @@ enum {
   HC_LOG10_MLOW,    // log10(m_low)
   HC_DLOG10_M,      // (log10 m_high - log10 m_low)/(rm-1)
   HC_LOG10_ZSTEP,   // (log10 z_max + 10)/(rc-2)
-  HC_DE_CONST       // 1 if w0==-1 && wa==0 (dark-energy term constant)
+  HC_DE_CONST,      // 1 if w0==-1 && wa==0 (dark-energy term constant)
+  // fp32 fast-path lookup constants (packed tables below)
+  HC_LUT_B0,        // float-bits bucket of dLt[1]:  (bits >> CHB_LUT_SHIFT)
+  HC_LUT_NB,        // number of buckets in use (0: fast path unavailable for this hyper-point)
+  HC_LG2_M0,        // log2(m_grid[0])
+  HC_INV_LG2_MSTEP, // (rm-1) / (log2 m_grid[rm-1] - log2 m_grid[0])
+  HC_LG2_Z1,        // log2(z_grid_interp[1]) = log2(1e-10)
+  HC_INV_LG2_ZSTEP  // (rc-2) / (log2 z_max - log2 1e-10)
 };
+#define CHB_LUT_SHIFT 19      // 16 buckets per octave of dL
+#define CHB_LUT_CAP 1024      // uint16 entries
 
 #define CHB_PI 3.141592653589793238462643383279502884
 #define CHB_DBL_MAX 1.7976931348623157e308
@@ -204,15 +213,30 @@ __device__ __forceinline__ double merger_rate(int rate_model, const double* __re
 // ------------------------------------------------------------------------------------------
 // per-hyper-point table block in global memory: [zg | iinv | dLt | mg | cdf], strides padded to
 // even counts so every sub-table is 16-byte aligned (bulk-copy requirement).
+//
+// fp32 fast-path block (same hyper-point, appended): float4 rows so that one LDS.128 brings the
+// knot, the value, the slope and the next knot:
+//   zi4[k] = {z_k, integral_invE_k, slope_k, z_{k+1}}      (index from log2 z: the grid is log-spaced)
+//   dl4[k] = {dL_k, z_k, dz/ddL slope_k, dL_{k+1}}         (index from a float-bits LUT + short scan)
+//   cd4[k] = {m_k, cdf_k, slope_k, m_{k+1}}                (index from log2 m)
+//   lut[b] = first candidate interval for dL in float-bits bucket b (uint16)
 struct TableLayout {
   int rc, rm;        // table resolutions
   int rcs, rms;      // padded strides
-  __host__ __device__ int total() const { return 3 * rcs + 2 * rms; }
+  __host__ __device__ int f64_total() const { return 3 * rcs + 2 * rms; }
   __host__ __device__ int off_zg() const { return 0; }
   __host__ __device__ int off_iinv() const { return rcs; }
   __host__ __device__ int off_dLt() const { return 2 * rcs; }
   __host__ __device__ int off_mg() const { return 3 * rcs; }
   __host__ __device__ int off_cdf() const { return 3 * rcs + rms; }
+  // fp32 block, offsets in doubles relative to the start of the hyper-point's table block
+  __host__ __device__ int off_f32() const { return f64_total(); }
+  __host__ __device__ int f32_zi4() const { return 0; }
+  __host__ __device__ int f32_dl4() const { return 2 * rcs; }
+  __host__ __device__ int f32_cd4() const { return 4 * rcs; }
+  __host__ __device__ int f32_lut() const { return 4 * rcs + 2 * rms; }
+  __host__ __device__ int f32_total() const { return 4 * rcs + 2 * rms + CHB_LUT_CAP / 4; }
+  __host__ __device__ int total() const { return f64_total() + f32_total(); }
 };
 static inline TableLayout make_layout(int rc, int rm) {
   TableLayout t;

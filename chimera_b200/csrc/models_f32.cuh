@@ -1,0 +1,128 @@
+// models_f32.cuh -- fp32 fast path of the population reweighting (CHB_FP32 mode).
+//
+// Same functions as models.cuh (pop_wrapper.py:67-80: z_from_dGW, theta_det2src, p_m1m2 / pe_prior)
+// evaluated in single precision on the FP32 + MUFU pipes instead of the FP64 pipe:
+//   * powers x^a as ex2(a * lg2 x) (MUFU.LG2 / MUFU.EX2), log2 of the detector-frame masses
+//     precomputed once at upload, so a source-frame mass power costs FADD + FMUL + MUFU;
+//   * table look-ups through the packed float4 rows of the fp32 table block (models.cuh):
+//     one LDS.128 per candidate interval; the dL -> z inversion finds its interval with a
+//     float-bits LUT and a short forward scan instead of an 11-step binary search;
+//   * the interpolants are the reference's own piecewise-linear functions on the reference's
+//     knots (knots and slopes are rounded from the fp64 tables), so the only deviations from the
+//     fp64 path are fp32 roundings (~1e-7 relative per sample); north_star budget for this mode: 1e-3.
+#pragma once
+#include "models.cuh"
+
+__device__ __forceinline__ float ex2f_(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2f_(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcpf_(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+#define CHB_LOG2E_F 1.4426950408889634f
+
+// per-hyper-point constants of the fast path, derived from the parameter row / HC row
+struct F32Consts {
+  // tables
+  const float4* zi4; const float4* dl4; const float4* cd4; const unsigned short* lut;
+  int rc, rm, nb; unsigned b0;
+  float lg2_m0, inv_lg2_mstep, lg2_z1, inv_lg2_zstep;
+  float z_last;
+  // mass
+  int mass_model;
+  float lo, hi, neg_alpha, beta, dm, inv_norm_p1;
+  float lam, mu, g_hi, g_c, g_pref, inv_plnorm;       // plp
+  float mb, neg_alpha2, ratio;                          // bpl
+};
+
+__device__ __forceinline__ F32Consts make_f32_consts(const ModelCfg& mc, const double* __restrict__ P,
+                                                     const double* __restrict__ HC, const double* __restrict__ f32blk) {
+  F32Consts c;
+  const TableLayout lay = mc.lay;
+  c.zi4 = reinterpret_cast<const float4*>(f32blk + lay.f32_zi4());
+  c.dl4 = reinterpret_cast<const float4*>(f32blk + lay.f32_dl4());
+  c.cd4 = reinterpret_cast<const float4*>(f32blk + lay.f32_cd4());
+  c.lut = reinterpret_cast<const unsigned short*>(f32blk + lay.f32_lut());
+  c.rc = lay.rc; c.rm = lay.rm;
+  c.nb = (int)HC[HC_LUT_NB]; c.b0 = (unsigned)HC[HC_LUT_B0];
+  c.lg2_m0 = (float)HC[HC_LG2_M0]; c.inv_lg2_mstep = (float)HC[HC_INV_LG2_MSTEP];
+  c.lg2_z1 = (float)HC[HC_LG2_Z1]; c.inv_lg2_zstep = (float)HC[HC_INV_LG2_ZSTEP];
+  c.z_last = (float)P[CHB_P_ZMAX];
+  c.mass_model = mc.mass_model;
+  c.lo = (float)P[CHB_P_MLOW]; c.hi = (float)P[CHB_P_MHIGH];
+  c.neg_alpha = (float)(-P[CHB_P_ALPHA]); c.beta = (float)P[CHB_P_BETA]; c.dm = (float)P[CHB_P_DELTAM];
+  c.inv_norm_p1 = (float)(1.0 / HC[HC_NORM_P_M1]);
+  c.lam = (float)P[CHB_P_LAMBDAP]; c.mu = (float)P[CHB_P_MUG];
+  const double sg = P[CHB_P_SIGMAG];
+  c.g_hi = (float)(P[CHB_P_MUG] + 5.0 * sg);
+  c.g_c = (float)(-1.4426950408889634 / (2.0 * sg * sg));
+  c.g_pref = (float)(1.0 / (sg * 2.5066282746310002 * HC[HC_TG_NORM]));
+  c.inv_plnorm = (float)(1.0 / HC[HC_PL_NORM]);
+  c.mb = (float)HC[HC_MBREAK]; c.neg_alpha2 = (float)(-P[CHB_P_ALPHA2]); c.ratio = (float)HC[HC_BPL_RATIO];
+  return c;
+}
+
+// z_from_dGW (cosmo.py:260-264): LUT bucket from the float bits, forward scan, one FFMA.
+__device__ __forceinline__ float z_from_dL_f32(const F32Consts& c, float dL) {
+  int b = (int)(__float_as_uint(dL) >> CHB_LUT_SHIFT) - (int)c.b0;
+  b = max(0, min(b, c.nb - 1));
+  int k = c.lut[b];
+  float4 e = c.dl4[k];
+  while (dL >= e.w && k < c.rc - 2) { ++k; e = c.dl4[k]; }
+  float z = fmaf(dL - e.x, e.z, e.y);
+  if (dL >= e.w) z = c.zi4[c.rc - 1].x;          // beyond the last knot: clamp (np.interp)
+  if (dL <= 0.f) z = 0.f;
+  return z;
+}
+
+// integral_invE at z by direct indexing of the log-spaced grid (cosmo.py:132-133)
+__device__ __forceinline__ float iinv_at_z_f32(const F32Consts& c, float z) {
+  int k = 0;
+  if (z > 1.0e-10f) k = 1 + (int)((lg2f_(z) - c.lg2_z1) * c.inv_lg2_zstep);
+  k = max(0, min(k, c.rc - 2));
+  float4 e = c.zi4[k];
+  if (z < e.x && k > 0) e = c.zi4[--k];          // one-step fix-up for index rounding
+  else if (z >= e.w && k < c.rc - 2) e = c.zi4[++k];
+  float v = fmaf(z - e.x, e.z, e.y);
+  if (z >= e.w) v = c.zi4[c.rc - 1].y;
+  return v;
+}
+
+// mass.py:255-264
+__device__ __forceinline__ float smoothing_f32(float m, float dm, float lo) {
+  const float x = m - lo;
+  if (x < 0.f) return 0.f;
+  if (x > dm) return 1.f;
+  const float t = dm * (rcpf_(x) + rcpf_(x - dm));
+  return rcpf_(1.f + ex2f_(t * CHB_LOG2E_F));
+}
+
+// p_m1m2 / pe_prior (mass.py:334-345, pop_wrapper.py:79).  lg2m1/lg2m2: log2 of the SOURCE-frame masses.
+__device__ __forceinline__ float weight_f32(const F32Consts& c, float m1, float m2, float lg2m1, float lg2m2,
+                                            float inv_prior) {
+  if (!(c.lo <= m1 && m1 <= c.hi)) return 0.f;        // primary support
+  float p1;
+  if (c.mass_model == CHB_MASS_TPL) {
+    p1 = ex2f_(c.neg_alpha * lg2m1);
+  } else if (c.mass_model == CHB_MASS_BPL) {
+    p1 = (m1 <= c.mb) ? ex2f_(c.neg_alpha * lg2m1) : 0.f;
+    if (m1 >= c.mb) p1 += ex2f_(c.neg_alpha2 * lg2m1) * c.ratio;
+    p1 *= smoothing_f32(m1, c.dm, c.lo);
+  } else {
+    const float Ppl = ex2f_(c.neg_alpha * lg2m1) * c.inv_plnorm;
+    const float d = m1 - c.mu;
+    const float G = (m1 <= c.g_hi) ? ex2f_(c.g_c * d * d) * c.g_pref : 0.f;
+    p1 = ((1.f - c.lam) * Ppl + c.lam * G) * smoothing_f32(m1, c.dm, c.lo);
+  }
+  // below ~1e-25 the term cannot matter next to any other sample, and the fp32 cdf would underflow
+  if (!(p1 > 1e-25f)) return 0.f;
+  if (!(c.lo <= m2 && m2 <= m1)) return 0.f;          // secondary support (tpl_notnorm(m2, beta, m_low, m1))
+  float p2 = ex2f_(c.beta * lg2m2);
+  if (c.mass_model != CHB_MASS_TPL) p2 *= smoothing_f32(m2, c.dm, c.lo);
+  int i = (int)((lg2m1 - c.lg2_m0) * c.inv_lg2_mstep);
+  i = max(0, min(i, c.rm - 2));
+  const float4 e = c.cd4[i];
+  float cdf = fmaf(m1 - e.x, e.z, e.y);
+  if (m1 >= c.cd4[c.rm - 1].x) cdf = c.cd4[c.rm - 1].y;
+  p2 = p2 * rcpf_(cdf);
+  if (p2 != p2) p2 = 0.f;                              // 0/0 -> 0 (mass.py:340)
+  return p1 * c.inv_norm_p1 * p2 * inv_prior;
+}

@@ -18,6 +18,7 @@
 // fp32 with one MUFU.EX2 per pair (Gaussian) or 3 FP32 ops (Epanechnikov), grid points held in
 // registers, samples broadcast from shared memory, warp-shuffle + fp64 cross-warp reduction.
 #include "common.cuh"
+#include "models_f32.cuh"
 #include "stage.cuh"
 
 #define NUM_THREADS 512
@@ -53,7 +54,7 @@ __host__ __device__ inline SmemPlan make_plan(int tab_total, int Nz, int B, int 
   return p;
 }
 size_t numerator_smem_bytes(const NumArgs& a, bool stage_in_smem) {
-  return (size_t)make_plan(a.mc.lay.total(), a.Nz, a.binning ? a.num_bins : 0, a.Ns, a.kind, stage_in_smem).total * sizeof(double);
+  return (size_t)make_plan(a.fp_mode == CHB_FP32 ? a.mc.lay.f32_total() : a.mc.lay.f64_total(), a.Nz, a.binning ? a.num_bins : 0, a.Ns, a.kind, stage_in_smem).total * sizeof(double);
 }
 long long numerator_scratch_doubles(const NumArgs& a) {
   return (long long)(a.kind == CHB_PGW_FULL ? 4 : 2) * a.Ns;
@@ -205,7 +206,10 @@ __device__ __forceinline__ double nan_to_num_log(double like) {
   return l;
 }
 
-template <bool STAGE_SMEM>
+// phase profile (only when a.prof != NULL): thread 0 stamps the SM clock at phase boundaries
+#define PHASE(i) do { if (a.prof && tid == 0) { long long _t = clock64(); pacc[i] += (unsigned long long)(_t - tlast); tlast = _t; } } while (0)
+
+template <bool STAGE_SMEM, bool F32>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 numerator_kernel(const NumArgs a) {
   extern __shared__ __align__(16) double sm[];
@@ -217,7 +221,9 @@ numerator_kernel(const NumArgs a) {
   const TableLayout lay = a.mc.lay;
   const int Ns = a.Ns, Nz = a.Nz, Pp = a.P, B = a.binning ? a.num_bins : 0;
   constexpr bool in_smem = STAGE_SMEM;
-  const SmemPlan pl = make_plan(lay.total(), Nz, B, Ns, a.kind, in_smem);
+  constexpr int fp_mode = F32 ? CHB_FP32 : CHB_FP64;
+  const int tab_total = F32 ? lay.f32_total() : lay.f64_total();
+  const SmemPlan pl = make_plan(tab_total, Nz, B, Ns, a.kind, in_smem);
   double* tab = sm + pl.tab;
   double* zgrid = sm + pl.zgrid;
   double* tw = sm + pl.tw;
@@ -247,13 +253,15 @@ numerator_kernel(const NumArgs a) {
   const int rc = lay.rc, rm = lay.rm;
   const int cm = a.mc.cosmo_model, mm = a.mc.mass_model, rmod = a.mc.rate_model;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t tab_bytes = (uint32_t)(lay.total() * sizeof(double));
+  const uint32_t tab_bytes = (uint32_t)(tab_total * sizeof(double));
   const bool pixelated = (a.kind != CHB_PGW_1D);
   const bool has_cat = (a.mc.catalog_kind == 1);
 
   if (tid == 0) mbar_init(&bar, 1);
   __syncthreads();
   uint32_t phase = 0;
+  unsigned long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tlast = clock64();
 
   const long long units = (long long)a.Nev * a.n_hyper;
   for (long long unit = blockIdx.x; unit < units; unit += gridDim.x) {
@@ -262,7 +270,7 @@ numerator_kernel(const NumArgs a) {
     if (tid == 0) {
       fence_proxy_async();
       mbar_expect_tx(&bar, tab_bytes);
-      bulk_g2s(tab, a.tabs + (size_t)h * lay.total(), tab_bytes, &bar);
+      bulk_g2s(tab, a.tabs + (size_t)h * lay.total() + (F32 ? lay.off_f32() : 0), tab_bytes, &bar);
     }
     if (tid < CHB_NPAR) P[tid] = a.hyper[(size_t)h * CHB_NPAR + tid];
     if (tid >= 64 && tid < 64 + CHB_NHC) HC[tid - 64] = a.HC[(size_t)h * CHB_NHC + tid - 64];
@@ -271,33 +279,60 @@ numerator_kernel(const NumArgs a) {
     __syncthreads();
     mbar_wait(&bar, phase);
     phase ^= 1;
+    PHASE(0);   // table staging + parameter loads
 
     // ---- z-grid quantities: Jacobian, dVc/dz, psi/(1+z), trapezoid weights --------------
+    F32Consts fc;
+    if constexpr (F32) fc = make_f32_consts(a.mc, P, HC, tab);
     for (int k = tid; k < Nz; k += NUM_THREADS) {
       const double z = zgrid[k];
-      const double dCt = dCt_from_dCr(P, HC, HC[HC_DH] * interp_clamped(z, zg, iinv, rc));
+      double ii;
+      if constexpr (F32) ii = (double)iinv_at_z_f32(fc, (float)z); else ii = interp_clamped(z, zg, iinv, rc);
+      const double dCt = dCt_from_dCr(P, HC, HC[HC_DH] * ii);
       const double Ez = E_at_z(P, HC, z);
       jac[k] = ddLdz_from(cm, P, HC, z, dCt, Ez) * ((1.0 + z) * (1.0 + z));   // likelihood.py:272,289
       dV[k] = dVcdz_from(HC, dCt, Ez);
       rj[k] = merger_rate(rmod, P, HC, z) / (1.0 + z);                        // pop_wrapper.py:85
       const double zl = (k > 0) ? zgrid[k - 1] : z, zr = (k < Nz - 1) ? zgrid[k + 1] : z;
       tw[k] = 0.5 * (zr - zl);                                                // trapezoid rule as a dot product
+      if constexpr (F32) rj[k] = rj[k] * tw[k] / jac[k];                      // one division per grid point, not per pixel
     }
 
+    PHASE(1);   // z-grid Jacobian / dVc/dz / rate
     // ---- stage 1: reweighting ----------------------------------------------------------
     const size_t so = (size_t)ev * Ns;
     double s1 = 0.0, s2 = 0.0, sz = 0.0, zmn = INFINITY, zmx = -INFINITY;
-    for (int j = tid; j < Ns; j += NUM_THREADS) {
-      const double dL = __ldg(a.dL + so + j);
-      const double z = interp_clamped(dL, dLt, zg, rc);
-      const double opz = 1.0 + z;
-      const double m1 = __ldg(a.m1d + so + j) / opz, m2 = __ldg(a.m2d + so + j) / opz;
-      const double w = p_m1m2(mm, P, HC, mg, cdf, rm, m1, m2) / __ldg(a.prior + so + j);
-      zs[j] = z;
-      ws[j] = w;
-      s1 += w; s2 += w * w; sz += z;
-      zmn = fmin(zmn, z); zmx = fmax(zmx, z);
+    if constexpr (F32) {
+      const float4* s4 = a.s4 + so;
+      const float2* l2 = a.l2 + so;
+#pragma unroll 2
+      for (int j = tid; j < Ns; j += NUM_THREADS) {
+        const float4 sv = __ldg(s4 + j);
+        const float2 lv = __ldg(l2 + j);
+        const float zf = z_from_dL_f32(fc, sv.x);
+        const float opz = 1.f + zf;
+        const float r = rcpf_(opz), lz = lg2f_(opz);
+        const float wf = weight_f32(fc, sv.y * r, sv.z * r, lv.x - lz, lv.y - lz, sv.w);
+        const double z = (double)zf, w = (double)wf;
+        zs[j] = z;
+        ws[j] = w;
+        s1 += w; s2 += w * w; sz += z;
+        zmn = fmin(zmn, z); zmx = fmax(zmx, z);
+      }
+    } else {
+      for (int j = tid; j < Ns; j += NUM_THREADS) {
+        const double dL = __ldg(a.dL + so + j);
+        const double z = interp_clamped(dL, dLt, zg, rc);
+        const double opz = 1.0 + z;
+        const double m1 = __ldg(a.m1d + so + j) / opz, m2 = __ldg(a.m2d + so + j) / opz;
+        const double w = p_m1m2(mm, P, HC, mg, cdf, rm, m1, m2) / __ldg(a.prior + so + j);
+        zs[j] = z;
+        ws[j] = w;
+        s1 += w; s2 += w * w; sz += z;
+        zmn = fmin(zmn, z); zmx = fmax(zmx, z);
+      }
     }
+    PHASE(2);   // reweighting loop (thread 0's share; includes waiting at the first reduction)
     s1 = block_sum(s1, red);
     s2 = block_sum(s2, red);
     sz = block_sum(sz, red);
@@ -337,6 +372,7 @@ numerator_kernel(const NumArgs a) {
     }
     __syncthreads();
 
+    PHASE(3);   // statistics + effective grid
     double like_acc = 0.0;      // per-thread partial of sum_p trapz_k(...)
     const double fR = HC[HC_FR];
     const double* pcat_ev = has_cat ? a.p_cat + (size_t)ev * Pp * Nz : nullptr;
@@ -376,7 +412,7 @@ numerator_kernel(const NumArgs a) {
       if (a.bw_method == CHB_BW_SCOTT) bw = pow(neff_k, -0.2) * dstd;
       else if (a.bw_method == CHB_BW_SILVERMAN) bw = pow(neff_k * 3.0 / 4.0, -0.2) * dstd;
       else bw = a.bw_value * dstd;
-      kde1d_any(a.fp_mode, const_cast<double*>(dx), dw, dn, a.binning ? xwb : reinterpret_cast<float2*>(zs), eg, G, bw, W,
+      kde1d_any(fp_mode, const_cast<double*>(dx), dw, dn, a.binning ? xwb : reinterpret_cast<float2*>(zs), eg, G, bw, W,
                 a.kernel, norm, part, dens);
       __syncthreads();
       for (int k = tid; k < Nz; k += NUM_THREADS) pgw[k] = interp_lr(zgrid[k], eg, dens, G, 0.0, 0.0);
@@ -384,19 +420,30 @@ numerator_kernel(const NumArgs a) {
       if (a.kind == CHB_PGW_1D) {
         for (int k = tid; k < Nz; k += NUM_THREADS) {
           const double pz = dV[k] * rj[k];
-          like_acc += (pgw[k] * pz / jac[k]) * tw[k];
+          if constexpr (F32) like_acc += pgw[k] * pz; else like_acc += (pgw[k] * pz / jac[k]) * tw[k];
           if (pout) pout[k] = pgw[k];
         }
       } else {
         const double* gwp = a.gw_pdf + (size_t)ev * Pp;
         if (pout) for (int i = tid; i < Pp * Nz; i += NUM_THREADS) pout[i] = pgw[i % Nz] * gwp[i / Nz];
-        for (int i = tid; i < npix * Nz; i += NUM_THREADS) {
-          const int p = i / Nz, k = i - p * Nz;
-          const double pc = has_cat ? pcat_ev[(size_t)p * Nz + k] : 0.0;
-          if (pc == -100.0) continue;            // likelihood.py:274 sentinel mask
-          const double pgal = has_cat ? fR * pc + (1.0 - pcompl_ev[k]) * dV[k] : dV[k];
-          const double pz = pgal * rj[k];
-          like_acc += ((pgw[k] * gwp[p]) * pz / jac[k]) * tw[k];
+        if (a.catA) {
+          // separable case: sum_p gw_pdf[p] p_gal[p,k] = fR A[k] + (1 - P_compl[k]) dVc/dz[k] B[k] with the
+          // hyper-independent pixel sums A, B precomputed once (the trapezoid rule and the pixel sum commute)
+          const double* A = a.catA + (size_t)ev * Nz;
+          const double* Bk = a.catB + (size_t)ev * Nz;
+          for (int k = tid; k < Nz; k += NUM_THREADS) {
+            const double pgs = has_cat ? fR * A[k] + (1.0 - pcompl_ev[k]) * dV[k] * Bk[k] : dV[k] * Bk[k];
+            if constexpr (F32) like_acc += pgw[k] * pgs * rj[k]; else like_acc += ((pgw[k] * pgs) * rj[k] / jac[k]) * tw[k];
+          }
+        } else {
+          for (int i = tid; i < npix * Nz; i += NUM_THREADS) {
+            const int p = i / Nz, k = i - p * Nz;
+            const double pc = has_cat ? pcat_ev[(size_t)p * Nz + k] : 0.0;
+            if (pc == -100.0) continue;            // likelihood.py:274 sentinel mask
+            const double pgal = has_cat ? fR * pc + (1.0 - pcompl_ev[k]) * dV[k] : dV[k];
+            const double pz = pgal * rj[k];
+            if constexpr (F32) like_acc += (pgw[k] * gwp[p]) * pz; else like_acc += ((pgw[k] * gwp[p]) * pz / jac[k]) * tw[k];
+          }
         }
       }
     } else if (a.kind == CHB_PGW_MARG) {
@@ -452,7 +499,7 @@ numerator_kernel(const NumArgs a) {
         else bw = a.bw_value * dstd;
         // W == 0 (no weight in the pixel) -> w/W = NaN for every sample in the reference
         const double scale = (W != 0.0) ? (norm * gwp[p]) : nan("");
-        kde1d_any(a.fp_mode, const_cast<double*>(dx), dw, dn, a.binning ? xwb : reinterpret_cast<float2*>(zs + o0), eg, G, bw, W,
+        kde1d_any(fp_mode, const_cast<double*>(dx), dw, dn, a.binning ? xwb : reinterpret_cast<float2*>(zs + o0), eg, G, bw, W,
                   CHB_KERNEL_EPAN, 1.0, part, dens);
         __syncthreads();
         for (int k = tid; k < Nz; k += NUM_THREADS) {
@@ -463,7 +510,7 @@ numerator_kernel(const NumArgs a) {
           if (pout) pout[(size_t)p * Nz + k] = v;
           if (pc == -100.0) continue;
           const double pgal = has_cat ? fR * pc + (1.0 - pcompl_ev[k]) * dV[k] : dV[k];
-          like_acc += (v * (pgal * rj[k]) / jac[k]) * tw[k];
+          if constexpr (F32) like_acc += v * (pgal * rj[k]); else like_acc += (v * (pgal * rj[k]) / jac[k]) * tw[k];
         }
         __syncthreads();
       }
@@ -509,7 +556,7 @@ numerator_kernel(const NumArgs a) {
       __syncthreads();
       const double l00 = L[0], l10 = L[1], l11 = L[2], l20 = L[3], l21 = L[4], l22 = L[5], lognorm = L[6];
       // whiten samples about the weighted mean: y = (x - mu)^T L ; weights normalised in place
-      const bool f32 = (a.fp_mode == CHB_FP32);
+      const bool f32 = (fp_mode == CHB_FP32);
       float4* yw = reinterpret_cast<float4*>(y1);      // fp32 mode: (y0,y1,y2,w') per sample over the y1|y2 region
       const double ps = 0.8493218002880191;            // sqrt(log2(e)/2): exp(-d^2/2) = 2^-(ps d)^2
       for (int j = tid; j < Ns; j += NUM_THREADS) {
@@ -553,7 +600,7 @@ numerator_kernel(const NumArgs a) {
             const double pc = has_cat ? pcat_ev[(size_t)p * Nz + k] : 0.0;
             if (pc != -100.0) {
               const double pgal = has_cat ? fR * pc + (1.0 - pcompl_ev[k]) * dV[k] : dV[k];
-              like_acc += (v * (pgal * rj[k]) / jac[k]) * tw[k];
+              if constexpr (F32) like_acc += v * (pgal * rj[k]); else like_acc += (v * (pgal * rj[k]) / jac[k]) * tw[k];
             }
           }
         }
@@ -599,25 +646,60 @@ numerator_kernel(const NumArgs a) {
             const double pc = has_cat ? pcat_ev[(size_t)p * Nz + k] : 0.0;
             if (pc != -100.0) {
               const double pgal = has_cat ? fR * pc + (1.0 - pcompl_ev[k]) * dV[k] : dV[k];
-              like_acc += (v * (pgal * rj[k]) / jac[k]) * tw[k];
+              if constexpr (F32) like_acc += v * (pgal * rj[k]); else like_acc += (v * (pgal * rj[k]) / jac[k]) * tw[k];
             }
           }
         }
       }
     }
 
+    PHASE(4);   // KDE + interpolation + integrand
     const double like = block_sum(like_acc, red);
     if (tid == 0) { a.log_like[(size_t)h * a.Nev + ev] = nan_to_num_log(like); a.like_raw[(size_t)h * a.Nev + ev] = like; }
+    PHASE(5);   // final reduction + store
   }
+  if (a.prof && tid == 0) for (int i = 0; i < 8; ++i) a.prof[(size_t)blockIdx.x * 8 + i] = pacc[i];
 }
 
 cudaError_t numerator_configure(size_t smem) {
-  cudaError_t e = cudaFuncSetAttribute(numerator_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(numerator_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(numerator_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(numerator_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(numerator_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+  return cudaFuncSetAttribute(numerator_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 cudaError_t launch_numerator(const NumArgs& a, int grid, int block, size_t smem, cudaStream_t s) {
-  if (a.scratch_stride == 0) numerator_kernel<true><<<grid, block, smem, s>>>(a);
-  else numerator_kernel<false><<<grid, block, smem, s>>>(a);
+  const bool in_smem = (a.scratch_stride == 0), f32 = (a.fp_mode == CHB_FP32);
+  if (in_smem && f32) numerator_kernel<true, true><<<grid, block, smem, s>>>(a);
+  else if (in_smem) numerator_kernel<true, false><<<grid, block, smem, s>>>(a);
+  else if (f32) numerator_kernel<false, true><<<grid, block, smem, s>>>(a);
+  else numerator_kernel<false, false><<<grid, block, smem, s>>>(a);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// Setup kernel for kind 'approximate': collapse the catalogue term over the event's pixels,
+//   A[ev,k] = sum_p gw_loc2d_pdf[ev,p] p_cat[ev,p,k],   B[ev,k] = sum_p gw_loc2d_pdf[ev,p] [p_cat[ev,p,k] != -100]
+// (p over valid pixels).  p_gw3d = p_gw1d[k] gw_pdf[p] is separable there (likelihood.py:150-154), so
+// sum_p trapz_k(p_gw3d p_z / jac) needs only A and B.  One coalesced pass over p_cat, once per run.
+__global__ void catalog_collapse_kernel(int Nev, int P, int Nz, const double* __restrict__ p_cat,
+                                        const double* __restrict__ gw_pdf, const int* __restrict__ neff_pix,
+                                        double* __restrict__ catA, double* __restrict__ catB) {
+  const int ev = blockIdx.x;
+  const int npix = neff_pix[ev];
+  for (int k = threadIdx.x; k < Nz; k += blockDim.x) {
+    double sa = 0.0, sb = 0.0;
+    for (int p = 0; p < npix; ++p) {
+      const double pc = p_cat[((size_t)ev * P + p) * Nz + k];
+      const double g = gw_pdf[(size_t)ev * P + p];
+      if (pc != -100.0) { sa += g * pc; sb += g; }
+    }
+    catA[(size_t)ev * Nz + k] = sa;
+    catB[(size_t)ev * Nz + k] = sb;
+  }
+}
+cudaError_t launch_catalog_collapse(int Nev, int P, int Nz, const double* p_cat, const double* gw_pdf, const int* neff_pix,
+                                   double* catA, double* catB, cudaStream_t s) {
+  catalog_collapse_kernel<<<Nev, 128, 0, s>>>(Nev, P, Nz, p_cat, gw_pdf, neff_pix, catA, catB);
   return cudaGetLastError();
 }

@@ -20,7 +20,7 @@ selection_kernel(SelArgs a) {
   __shared__ double red[32];
   const TableLayout lay = a.mc.lay;
   const int h = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
-  const uint32_t tab_bytes = (uint32_t)(lay.total() * sizeof(double));
+  const uint32_t tab_bytes = (uint32_t)(lay.f64_total() * sizeof(double));
 
   if (tid == 0) mbar_init(&bar, 1);
   __syncthreads();
@@ -69,7 +69,7 @@ selection_kernel(SelArgs a) {
 }
 
 cudaError_t launch_selection(const SelArgs& a, cudaStream_t s) {
-  size_t smem = (size_t)a.mc.lay.total() * sizeof(double);
+  size_t smem = (size_t)a.mc.lay.f64_total() * sizeof(double);
   cudaError_t e = cudaFuncSetAttribute(selection_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   dim3 grid(a.tiles, a.n_hyper);

@@ -124,6 +124,48 @@ build_tables_kernel(ModelCfg mc, int n_hyper, const double* __restrict__ hyper, 
     T[mc.lay.off_mg() + i] = ms[i];
     T[mc.lay.off_cdf() + i] = p2[i];
   }
+  // ---- fp32 fast-path block: packed float4 rows + float-bits LUT -----------------------------
+  {
+    float4* zi4 = reinterpret_cast<float4*>(T + mc.lay.off_f32() + mc.lay.f32_zi4());
+    float4* dl4 = reinterpret_cast<float4*>(T + mc.lay.off_f32() + mc.lay.f32_dl4());
+    float4* cd4 = reinterpret_cast<float4*>(T + mc.lay.off_f32() + mc.lay.f32_cd4());
+    unsigned short* lut = reinterpret_cast<unsigned short*>(T + mc.lay.off_f32() + mc.lay.f32_lut());
+    const double* dLg = T + mc.lay.off_dLt();       // written above by this CTA
+    __syncthreads();
+    for (int i = tid; i < rc; i += nt) {
+      const int j = min(i + 1, rc - 1);
+      const double z0 = zs[i], z1 = zs[j], d0 = dLg[i], d1 = dLg[j];
+      const double si = (z1 > z0) ? (ys[j] - ys[i]) / (z1 - z0) : 0.0;
+      const double sd = (d1 != d0) ? (z1 - z0) / (d1 - d0) : 0.0;
+      zi4[i] = make_float4((float)z0, (float)ys[i], (float)si, (float)z1);
+      dl4[i] = make_float4((float)d0, (float)z0, (float)sd, (float)d1);
+    }
+    for (int i = tid; i < rm; i += nt) {
+      const int j = min(i + 1, rm - 1);
+      const double m0 = ms[i], m1 = ms[j];
+      const double sc = (m1 > m0) ? (p2[j] - p2[i]) / (m1 - m0) : 0.0;
+      cd4[i] = make_float4((float)m0, (float)p2[i], (float)sc, (float)m1);
+    }
+    // LUT over float-bits buckets of dL: lut[b] = last knot k with dLt[k] <= lower edge of bucket b
+    const unsigned b0 = __float_as_uint((float)dLg[1]) >> CHB_LUT_SHIFT;
+    const unsigned b1 = __float_as_uint((float)dLg[rc - 1]) >> CHB_LUT_SHIFT;
+    const bool lut_ok = (dLg[1] > 0.0) && (b1 >= b0) && (b1 - b0 + 2 <= CHB_LUT_CAP) && (rc <= 65535);
+    const int nb = lut_ok ? (int)(b1 - b0 + 2) : 0;
+    for (int b = tid; b < nb; b += nt) {
+      const double edge = (double)__uint_as_float((b0 + (unsigned)b) << CHB_LUT_SHIFT);
+      int k = upper_index(dLg, rc, edge) - 1;       // dLt[k] <= edge < dLt[k+1] (clamped)
+      if (b == 0) k = 0;
+      lut[b] = (unsigned short)max(0, min(k, rc - 2));
+    }
+    if (tid == 0) {
+      HC[HC_LUT_B0] = (double)b0;
+      HC[HC_LUT_NB] = (double)nb;
+      HC[HC_LG2_M0] = log2(ms[0]);
+      HC[HC_INV_LG2_MSTEP] = (double)(rm - 1) / (log2(ms[rm - 1]) - log2(ms[0]));
+      HC[HC_LG2_Z1] = log2(zs[1]);
+      HC[HC_INV_LG2_ZSTEP] = (double)(rc - 2) / (log2(zs[rc - 1]) - log2(zs[1]));
+    }
+  }
   if (tid == 0 && mc.catalog_kind == 1) {   // fR = Vc(z_hi) - Vc(z_lo)  (completeness.py:54-58)
     double dlo = dCt_from_dCr(P, HC, HC[HC_DH] * interp_clamped(mc.compl_z_lo, zs, ys, rc));
     double dhi = dCt_from_dCr(P, HC, HC[HC_DH] * interp_clamped(mc.compl_z_hi, zs, ys, rc));

@@ -103,6 +103,13 @@ class Engine:
                                      *[_lib.dptr(o) for o in outs]))
     return dict(log_like_num=outs[0], log_Nexp=outs[1], log_hyper=outs[2], neff_inj=outs[3], N_exp=outs[4])
 
+  def phase_profile(self, enable=True):
+    """Mean SM cycles per CTA in each phase of the numerator kernel (last profiled evaluation)."""
+    out = np.zeros(8)
+    self._chk(self.lib.chb_phase_profile(self.h, int(enable), _lib.dptr(out)))
+    names = ("tables", "zgrid", "reweight", "stats", "kde_integrand", "final")
+    return {k: float(v) for k, v in zip(names, out)}
+
   @property
   def launches(self):
     return int(self.lib.chb_kernel_launch_count(self.h))

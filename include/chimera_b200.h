@@ -188,6 +188,12 @@ int64_t chb_kernel_launch_count(const chb_handle* h);
  * out[0]=tables, out[1]=numerator (reweight+KDE+z-integral), out[2]=selection, out[3]=reduce */
 int chb_last_timings(const chb_handle* h, double out[4]);
 
+/* Phase profile of the fused numerator kernel: mean SM-clock cycles per CTA spent in
+ * [0] table staging, [1] z-grid terms, [2] reweighting, [3] statistics/grid, [4] KDE+integrand,
+ * [5] final reduction, for the most recent evaluation run with profiling enabled.  `enable`
+ * switches collection on/off for the following evaluations; `out` may be NULL. */
+int chb_phase_profile(chb_handle* h, int enable, double out[8]);
+
 /* Measured MUFU.EX2 throughput [exp/s] of `device` (micro-benchmark run for ~`seconds`): the
  * denominator of the KDE roofline fraction. */
 int chb_mufu_peak(int device, double seconds, double* exp_per_s);
