@@ -62,6 +62,8 @@ struct chb_handle {
   bool cat_collapsed = false;
   bool want_prof = false;
   DevBuf<double> inj_m1, inj_m2, inj_dL, inj_pd;
+  DevBuf<float4> inj_s4;
+  DevBuf<float2> inj_l2;
   // per-eval buffers
   DevBuf<double> hyper, tabs, HC, log_like, like_raw, tile_part, partials, pgw, scratch;
   int64_t last_n_hyper = 0;
@@ -153,7 +155,7 @@ void chb_destroy(chb_handle* h) {
   for (auto* b : dbl) b->release();
   h->pix_off.release();
   h->prof.release();
-  h->s4.release(); h->l2.release(); h->catA.release(); h->catB.release();
+  h->s4.release(); h->l2.release(); h->inj_s4.release(); h->inj_l2.release(); h->catA.release(); h->catB.release();
   h->neff_pix.release();
   for (auto& evn : h->ev) if (evn) cudaEventDestroy(evn);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -233,6 +235,16 @@ int chb_set_injections(chb_handle* h, int64_t Ninj, const double* m1det, const d
   CU(h->inj_m2.upload(m2det, Ninj), "upload inj m2det");
   CU(h->inj_dL.upload(dL, Ninj), "upload inj dL");
   CU(h->inj_pd.upload(p_draw, Ninj), "upload inj p_draw");
+  if (h->cfg.fp_mode == CHB_FP32) {
+    std::vector<float4> s4(Ninj);
+    std::vector<float2> l2(Ninj);
+    for (int64_t i = 0; i < Ninj; ++i) {
+      s4[i] = make_float4((float)dL[i], (float)m1det[i], (float)m2det[i], (float)(1.0 / p_draw[i]));
+      l2[i] = make_float2((float)std::log2(m1det[i]), (float)std::log2(m2det[i]));
+    }
+    CU(h->inj_s4.upload(s4.data(), Ninj), "upload packed injections");
+    CU(h->inj_l2.upload(l2.data(), Ninj), "upload injection log2 masses");
+  }
   h->Ninj = Ninj; h->have_inj = true;
   return CHB_OK;
 }
@@ -388,6 +400,7 @@ static int eval_impl(chb_handle* h, int64_t n_hyper, const double* d_hyper, doub
     SelArgs sa;
     sa.mc = h->mc; sa.Ninj = (int)h->Ninj; sa.n_hyper = (int)n_hyper; sa.tiles = tiles;
     sa.m1d = h->inj_m1.p; sa.m2d = h->inj_m2.p; sa.dL = h->inj_dL.p; sa.p_draw = h->inj_pd.p;
+    sa.fp_mode = c.fp_mode; sa.s4 = h->inj_s4.p; sa.l2 = h->inj_l2.p;
     sa.hyper = d_hyper; sa.tabs = h->tabs.p; sa.HC = h->HC.p; sa.tile_part = h->tile_part.p;
     CU(launch_selection(sa, s), "selection launch");
     h->launches++;

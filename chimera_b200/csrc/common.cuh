@@ -51,6 +51,9 @@ struct SelArgs {
   ModelCfg mc;
   int Ninj, n_hyper, tiles;
   const double *m1d, *m2d, *dL, *p_draw;
+  int fp_mode;
+  const float4* s4;      // fp32 mode: {dL, m1det, m2det, 1/p_draw}
+  const float2* l2;      //            {log2 m1det, log2 m2det}
   const double *hyper, *tabs, *HC;
   double* tile_part;     // (n_hyper, tiles, 2): nansum(w), sum(w^2) per tile
 };

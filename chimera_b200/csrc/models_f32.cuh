@@ -126,3 +126,56 @@ __device__ __forceinline__ float weight_f32(const F32Consts& c, float m1, float 
   if (p2 != p2) p2 = 0.f;                              // 0/0 -> 0 (mass.py:340)
   return p1 * c.inv_norm_p1 * p2 * inv_prior;
 }
+
+// ------------------------------------------------------------------------------------------
+// cosmology / rate terms of the detector-frame rate (pop_wrapper.py:102-111) in single precision
+struct CosmoRateF32 {
+  int cosmo_model, rate_model;
+  float Om, Or, Ok, Ode, w0, wa, dH, Xi0, n, R0;
+  bool de_const;
+  float gamma, gk, lg2_opzp, rnorm, rzmax;
+};
+__device__ __forceinline__ CosmoRateF32 make_cosmo_rate_f32(const ModelCfg& mc, const double* __restrict__ P,
+                                                            const double* __restrict__ HC) {
+  CosmoRateF32 c;
+  c.cosmo_model = mc.cosmo_model; c.rate_model = mc.rate_model;
+  c.Om = (float)P[CHB_P_OM0]; c.Or = (float)P[CHB_P_OR0]; c.Ok = (float)P[CHB_P_OK0]; c.Ode = (float)HC[HC_ODE0];
+  c.w0 = (float)P[CHB_P_W0]; c.wa = (float)P[CHB_P_WA]; c.dH = (float)HC[HC_DH];
+  c.Xi0 = (float)P[CHB_P_XI0]; c.n = (float)P[CHB_P_N]; c.R0 = (float)P[CHB_P_R0];
+  c.de_const = HC[HC_DE_CONST] != 0.0;
+  c.gamma = (float)P[CHB_P_GAMMA]; c.gk = (float)(P[CHB_P_GAMMA] + P[CHB_P_KAPPA]);
+  c.lg2_opzp = (float)log2(1.0 + P[CHB_P_ZP]); c.rnorm = (float)HC[HC_RATE_NORM]; c.rzmax = (float)P[CHB_P_RZMAX];
+  return c;
+}
+// E(z) (cosmo.py:122-130); lz = log2(1+z)
+__device__ __forceinline__ float E_at_z_f32(const CosmoRateF32& c, float z, float opz, float lz) {
+  const float x2 = opz * opz;
+  float de = 1.f;
+  if (!c.de_const) de = ex2f_(3.f * (1.f + c.w0 + c.wa * z * rcpf_(opz)) * lz);
+  return sqrtf(c.Om * (x2 * opz) + c.Or * (x2 * x2) + c.Ok * x2 + c.Ode * de);
+}
+// merger_rate (rate.py:96-129)
+__device__ __forceinline__ float merger_rate_f32(const CosmoRateF32& c, float z, float lz) {
+  const float pl = ex2f_(c.gamma * lz);
+  if (c.rate_model == CHB_RATE_POWER_LAW) return pl;
+  if (c.rate_model == CHB_RATE_TRUNC_PL) return (z < c.rzmax) ? pl * c.rnorm : 0.f;
+  const float v = c.rnorm * pl * rcpf_(1.f + ex2f_(c.gk * (lz - c.lg2_opzp)));
+  if (c.rate_model == CHB_RATE_TRUNC_MD) return (z < c.rzmax) ? v : 0.f;
+  return v;
+}
+// dN/dtheta_det / (R0 p_m1m2) for an injection with its ORIGINAL distance dL (pop_wrapper.py:105-110):
+// dVc/dz psi/(1+z) / (|ddL/dz| (1+z)^2)
+__device__ __forceinline__ float zterm_inj_f32(const CosmoRateF32& c, float z, float opz, float lz, float dL) {
+  float Xi = 1.f, dCt = dL * rcpf_(opz);
+  if (c.cosmo_model == CHB_COSMO_MG_FLRW) {
+    Xi = c.Xi0 + (1.f - c.Xi0) * ex2f_(-c.n * lz);
+    dCt = dCt * rcpf_(Xi);
+  }
+  const float Ez = E_at_z_f32(c, z, opz, lz);
+  const float dHE = c.dH * rcpf_(Ez);
+  float ddL = dCt + dHE * opz;
+  if (c.cosmo_model == CHB_COSMO_MG_FLRW)
+    ddL = ddL * Xi + (dCt * opz) * (c.n * (c.Xi0 - 1.f) * ex2f_(-(c.n + 1.f) * lz));
+  const float dV = 12.566370614359172f * dHE * dCt * dCt;
+  return dV * merger_rate_f32(c, z, lz) * rcpf_(opz) * rcpf_(fabsf(ddL) * opz * opz);
+}

@@ -9,6 +9,7 @@
 // with coalesced 8-byte loads, and writes one (S1,S2) pair; reduce.cu adds the tiles in a fixed
 // order, so results are bit-reproducible run to run.  fp64 throughout.
 #include "common.cuh"
+#include "models_f32.cuh"
 #include "stage.cuh"
 
 __global__ void __launch_bounds__(256)
@@ -68,7 +69,77 @@ selection_kernel(SelArgs a) {
   }
 }
 
+// fp32 variant (CHB_FP32): same reduction, the per-injection rate evaluated with the fp32 fast path
+// (models_f32.cuh); only the dl4 | cd4 | lut part of the fp32 table block is staged (42 KB); sums
+// accumulate in fp64.
+__global__ void __launch_bounds__(256)
+selection_f32_kernel(SelArgs a) {
+  extern __shared__ __align__(16) double sm[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ double P[CHB_NPAR];
+  __shared__ double HC[CHB_NHC];
+  __shared__ double red[32];
+  const TableLayout lay = a.mc.lay;
+  const int h = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
+  const int part_off = lay.f32_dl4();
+  const uint32_t tab_bytes = (uint32_t)((lay.f32_total() - part_off) * sizeof(double));
+  if (tid == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&bar, tab_bytes);
+    bulk_g2s(sm, a.tabs + (size_t)h * lay.total() + lay.off_f32() + part_off, tab_bytes, &bar);
+  }
+  if (tid < CHB_NPAR) P[tid] = a.hyper[(size_t)h * CHB_NPAR + tid];
+  if (tid < CHB_NHC) HC[tid] = a.HC[(size_t)h * CHB_NHC + tid];
+  __syncthreads();
+  mbar_wait(&bar, 0);
+  const F32Consts fc = make_f32_consts(a.mc, P, HC, sm - part_off);   // zi4 (not staged) is never touched here
+  const CosmoRateF32 cr = make_cosmo_rate_f32(a.mc, P, HC);
+  const float z_top = (float)a.tabs[(size_t)h * lay.total() + lay.off_zg() + lay.rc - 1];
+
+  const long long chunk = ((long long)a.Ninj + a.tiles - 1) / a.tiles;
+  const long long j0 = (long long)tile * chunk;
+  const long long j1 = min((long long)a.Ninj, j0 + chunk);
+  double s1 = 0.0, s2 = 0.0;
+#pragma unroll 2
+  for (long long j = j0 + tid; j < j1; j += blockDim.x) {
+    const float4 sv = __ldg(a.s4 + j);
+    const float2 lv = __ldg(a.l2 + j);
+    // z_from_dGW without the zi4 clamp row: same scan, clamp with the staged last knot
+    int b = (int)(__float_as_uint(sv.x) >> CHB_LUT_SHIFT) - (int)fc.b0;
+    b = max(0, min(b, fc.nb - 1));
+    int k = fc.lut[b];
+    float4 e = fc.dl4[k];
+    while (sv.x >= e.w && k < fc.rc - 2) { ++k; e = fc.dl4[k]; }
+    float z = fmaf(sv.x - e.x, e.z, e.y);
+    if (sv.x >= e.w) z = z_top;
+    if (sv.x <= 0.f) z = 0.f;
+    const float opz = 1.f + z;
+    const float r = rcpf_(opz), lz = lg2f_(opz);
+    const float pm = weight_f32(fc, sv.y * r, sv.z * r, lv.x - lz, lv.y - lz, sv.w);   // p_m1m2 / p_draw
+    const float wf = cr.R0 * pm * zterm_inj_f32(cr, z, opz, lz, sv.x);
+    const double w = (double)wf;
+    if (wf == wf) s1 += w;
+    s2 += w * w;
+  }
+  s1 = block_sum(s1, red);
+  s2 = block_sum(s2, red);
+  if (tid == 0) {
+    double* out = a.tile_part + ((size_t)h * a.tiles + tile) * 2;
+    out[0] = s1;
+    out[1] = s2;
+  }
+}
+
 cudaError_t launch_selection(const SelArgs& a, cudaStream_t s) {
+  if (a.fp_mode == CHB_FP32) {
+    size_t smem32 = (size_t)(a.mc.lay.f32_total() - a.mc.lay.f32_dl4()) * sizeof(double);
+    cudaError_t e32 = cudaFuncSetAttribute(selection_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
+    if (e32 != cudaSuccess) return e32;
+    dim3 grid32(a.tiles, a.n_hyper);
+    selection_f32_kernel<<<grid32, 256, smem32, s>>>(a);
+    return cudaGetLastError();
+  }
   size_t smem = (size_t)a.mc.lay.f64_total() * sizeof(double);
   cudaError_t e = cudaFuncSetAttribute(selection_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
