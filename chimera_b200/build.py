@@ -6,8 +6,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libchimera_b200.so")
-SOURCES = ["tables.cu", "selection.cu", "numerator.cu", "api.cu", "microbench.cu"]
-HEADERS = ["models.cuh", "models_f32.cuh", "common.cuh", "stage.cuh", os.path.join("..", "..", "include", "chimera_b200.h")]
+SOURCES = ["tables.cu", "selection.cu", "numerator.cu", "numerator_f32.cu", "api.cu", "microbench.cu"]
+HEADERS = ["models.cuh", "models_f32.cuh", "kde_f32.cuh", "common.cuh", "stage.cuh", os.path.join("..", "..", "include", "chimera_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 

@@ -369,23 +369,41 @@ static int eval_impl(chb_handle* h, int64_t n_hyper, const double* d_hyper, doub
     a.log_like = ll; a.like_raw = h->like_raw.p; a.p_gw_out = d_pgw;
     h->last_n_hyper = n_hyper;
     if (c.kind_p_gw == CHB_PGW_MARG && !h->pix_off.p) return fail(h, CHB_ERR_STATE, "marginalized kind needs pixels_pe_opt_nside");
-    // sample staging in shared memory when it fits, else per-CTA global scratch (L2-resident)
-    size_t smem = numerator_smem_bytes(a, true);
-    h->stage_in_smem = smem <= (size_t)h->max_smem_optin;
-    if (!h->stage_in_smem) smem = numerator_smem_bytes(a, false);
-    if (smem > (size_t)h->max_smem_optin) return fail(h, CHB_ERR_UNSUPPORTED, "z grid / tables do not fit in shared memory");
-    CU(numerator_configure(smem), "numerator smem opt-in");
     const long long units = (long long)h->Nev * n_hyper;
-    int grid = (int)std::min<long long>(units, (long long)h->sm_count);
-    if (!h->stage_in_smem) {
-      a.scratch_stride = numerator_scratch_doubles(a);
-      CU(h->scratch.alloc((size_t)grid * a.scratch_stride), "alloc staging scratch");
-      a.scratch = h->scratch.p;
-    }
-    h->num_grid = grid; h->num_smem = smem;
     a.prof = nullptr;
-    if (h->want_prof) { CU(h->prof.alloc((size_t)grid * 8), "alloc profile"); a.prof = h->prof.p; }
-    CU(launch_numerator(a, grid, numerator_block_threads(), smem, s), "numerator launch");
+    bool fast = false;
+    if (c.fp_mode == CHB_FP32) {
+      // fast path: 256-thread CTAs, float2 staging; two CTAs per SM when the plan fits in ~113 KB
+      size_t fs = numerator_f32_smem_bytes(a);
+      if (fs <= (size_t)h->max_smem_optin) {
+        CU(numerator_f32_configure(fs), "numerator_f32 smem opt-in");
+        int per_sm = numerator_f32_ctas_per_sm(fs);
+        if (per_sm >= 1) {
+          int grid = (int)std::min<long long>(units, (long long)h->sm_count * per_sm);
+          h->num_grid = grid; h->num_smem = fs;
+          if (h->want_prof) { CU(h->prof.alloc((size_t)grid * 8), "alloc profile"); a.prof = h->prof.p; }
+          CU(launch_numerator_f32(a, grid, fs, s), "numerator_f32 launch");
+          fast = true;
+        }
+      }
+    }
+    if (!fast) {
+      // generic kernel: sample staging in shared memory when it fits, else per-CTA global scratch (L2-resident)
+      size_t smem = numerator_smem_bytes(a, true);
+      h->stage_in_smem = smem <= (size_t)h->max_smem_optin;
+      if (!h->stage_in_smem) smem = numerator_smem_bytes(a, false);
+      if (smem > (size_t)h->max_smem_optin) return fail(h, CHB_ERR_UNSUPPORTED, "z grid / tables do not fit in shared memory");
+      CU(numerator_configure(smem), "numerator smem opt-in");
+      int grid = (int)std::min<long long>(units, (long long)h->sm_count);
+      if (!h->stage_in_smem) {
+        a.scratch_stride = numerator_scratch_doubles(a);
+        CU(h->scratch.alloc((size_t)grid * a.scratch_stride), "alloc staging scratch");
+        a.scratch = h->scratch.p;
+      }
+      h->num_grid = grid; h->num_smem = smem;
+      if (h->want_prof) { CU(h->prof.alloc((size_t)grid * 8), "alloc profile"); a.prof = h->prof.p; }
+      CU(launch_numerator(a, grid, numerator_block_threads(), smem, s), "numerator launch");
+    }
     h->launches++;
   }
   cudaEventRecord(h->ev[2], s);

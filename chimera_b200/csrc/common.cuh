@@ -67,6 +67,10 @@ size_t numerator_smem_bytes(const NumArgs& a, bool stage_in_smem);
 long long numerator_scratch_doubles(const NumArgs& a);
 int numerator_block_threads();
 cudaError_t numerator_configure(size_t smem);
+size_t numerator_f32_smem_bytes(const NumArgs& a);
+cudaError_t numerator_f32_configure(size_t smem);
+int numerator_f32_ctas_per_sm(size_t smem);
+cudaError_t launch_numerator_f32(const NumArgs& a, int grid, size_t smem, cudaStream_t s);
 cudaError_t launch_catalog_collapse(int Nev, int P, int Nz, const double* p_cat, const double* gw_pdf, const int* neff_pix,
                                    double* catA, double* catB, cudaStream_t s);
 cudaError_t launch_reduce(int n_hyper, int Nev, int tiles, const double* d_log_like, const double* d_tile_part,

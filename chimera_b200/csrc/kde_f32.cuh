@@ -1,0 +1,86 @@
+// kde_f32.cuh -- fp32 KDE pair sums shared by the numerator kernels.
+#pragma once
+#include "models.cuh"
+
+// 2^x on the MUFU pipe, flush-to-zero: no range fix-up code around the instruction (exp2f() adds an
+// FSETP and two predicated FMULs per call to keep denormal results, which are irrelevant here).
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int R, int NW>
+__device__ __forceinline__ void kde1d_f32_pass(const float2* __restrict__ xw, int n, const double* __restrict__ eg,
+                                               int G, int g_base, double c, double s, int kernel,
+                                               float* __restrict__ part /* [NW][G] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float gp[R], acc[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    int g = g_base + r * 32 + lane;
+    gp[r] = (g < G) ? (float)((eg[g] - c) * s) : 3.0e18f;   // far away: contributes exactly 0
+    acc[r] = 0.f;
+  }
+  const int per = (n + NW - 1) / NW;
+  const int j0 = min(n, warp * per), j1 = min(n, j0 + per);
+  if (kernel == CHB_KERNEL_GAUSS) {
+#pragma unroll 4
+    for (int j = j0; j < j1; ++j) {
+      const float2 v = xw[j];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float d = gp[r] - v.x;
+        acc[r] = fmaf(v.y, ex2_ftz(-(d * d)), acc[r]);
+      }
+    }
+  } else {
+#pragma unroll 4
+    for (int j = j0; j < j1; ++j) {
+      const float2 v = xw[j];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float d = gp[r] - v.x;
+        acc[r] = fmaf(v.y, fmaxf(fmaf(-d, d, 1.f), 0.f), acc[r]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    int g = g_base + r * 32 + lane;
+    if (g < G) part[warp * G + g] = acc[r];
+  }
+}
+
+// dens[g] = scale * sum_j w'_j K(g' - x'_j).  Must be called by the whole CTA (NW warps).
+template <int NW>
+__device__ __forceinline__ void kde1d_f32(const float2* __restrict__ xw, int n, const double* __restrict__ eg, int G,
+                                          double c, double s, int kernel, double scale, float* __restrict__ part,
+                                          double* __restrict__ dens) {
+  // register tile height: fewest (passes x R), larger R on ties
+  int R = 1, best = 1 << 30;
+  for (int r = 8; r >= 1; --r) {
+    int cost = ((G + 32 * r - 1) / (32 * r)) * r;
+    if (cost < best) { best = cost; R = r; }
+  }
+  for (int gb = 0; gb < G; gb += 32 * R) {
+    switch (R) {
+      case 1: kde1d_f32_pass<1, NW>(xw, n, eg, G, gb, c, s, kernel, part); break;
+      case 2: kde1d_f32_pass<2, NW>(xw, n, eg, G, gb, c, s, kernel, part); break;
+      case 3: kde1d_f32_pass<3, NW>(xw, n, eg, G, gb, c, s, kernel, part); break;
+      case 4: kde1d_f32_pass<4, NW>(xw, n, eg, G, gb, c, s, kernel, part); break;
+      case 5: kde1d_f32_pass<5, NW>(xw, n, eg, G, gb, c, s, kernel, part); break;
+      case 6: kde1d_f32_pass<6, NW>(xw, n, eg, G, gb, c, s, kernel, part); break;
+      case 7: kde1d_f32_pass<7, NW>(xw, n, eg, G, gb, c, s, kernel, part); break;
+      default: kde1d_f32_pass<8, NW>(xw, n, eg, G, gb, c, s, kernel, part); break;
+    }
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < G; g += NW * 32) {
+    double acc = 0.0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) acc += (double)part[w * G + g];
+    dens[g] = acc * scale;
+  }
+}
+

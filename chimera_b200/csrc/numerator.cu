@@ -19,6 +19,7 @@
 // registers, samples broadcast from shared memory, warp-shuffle + fp64 cross-warp reduction.
 #include "common.cuh"
 #include "models_f32.cuh"
+#include "kde_f32.cuh"
 #include "stage.cuh"
 
 #define NUM_THREADS 512
@@ -95,87 +96,6 @@ __device__ __forceinline__ void kde1d_f64(const double* __restrict__ x, const do
 // in registers; all lanes of a warp read the same sample (one broadcast LDS.64 per R pairs); the 16
 // warps split the samples; per-warp partial sums are combined in fp64.  Per pair the Gaussian costs
 // FADD + FMUL + MUFU.EX2 + FFMA: the loop is bound by the MUFU pipe (16 ex2/clk/SM).
-// 2^x on the MUFU pipe, flush-to-zero: no range fix-up code around the instruction (exp2f() adds an
-// FSETP and two predicated FMULs per call to keep denormal results, which are irrelevant here).
-__device__ __forceinline__ float ex2_ftz(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-template <int R>
-__device__ __forceinline__ void kde1d_f32_pass(const float2* __restrict__ xw, int n, const double* __restrict__ eg,
-                                               int G, int g_base, double c, double s, int kernel,
-                                               float* __restrict__ part /* [NUM_WARPS][G] */) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float gp[R], acc[R];
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    int g = g_base + r * 32 + lane;
-    gp[r] = (g < G) ? (float)((eg[g] - c) * s) : 3.0e18f;   // far away: contributes exactly 0
-    acc[r] = 0.f;
-  }
-  const int per = (n + NUM_WARPS - 1) / NUM_WARPS;
-  const int j0 = min(n, warp * per), j1 = min(n, j0 + per);
-  if (kernel == CHB_KERNEL_GAUSS) {
-#pragma unroll 4
-    for (int j = j0; j < j1; ++j) {
-      const float2 v = xw[j];
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const float d = gp[r] - v.x;
-        acc[r] = fmaf(v.y, ex2_ftz(-(d * d)), acc[r]);
-      }
-    }
-  } else {
-#pragma unroll 4
-    for (int j = j0; j < j1; ++j) {
-      const float2 v = xw[j];
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const float d = gp[r] - v.x;
-        acc[r] = fmaf(v.y, fmaxf(fmaf(-d, d, 1.f), 0.f), acc[r]);
-      }
-    }
-  }
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    int g = g_base + r * 32 + lane;
-    if (g < G) part[warp * G + g] = acc[r];
-  }
-}
-
-// dens[g] = scale * sum_j w'_j K(g' - x'_j).  Must be called by the whole CTA.
-__device__ __forceinline__ void kde1d_f32(const float2* __restrict__ xw, int n, const double* __restrict__ eg, int G,
-                                          double c, double s, int kernel, double scale, float* __restrict__ part,
-                                          double* __restrict__ dens) {
-  // register tile height: fewest (passes x R), larger R on ties
-  int R = 1, best = 1 << 30;
-  for (int r = 8; r >= 1; --r) {
-    int cost = ((G + 32 * r - 1) / (32 * r)) * r;
-    if (cost < best) { best = cost; R = r; }
-  }
-  for (int gb = 0; gb < G; gb += 32 * R) {
-    switch (R) {
-      case 1: kde1d_f32_pass<1>(xw, n, eg, G, gb, c, s, kernel, part); break;
-      case 2: kde1d_f32_pass<2>(xw, n, eg, G, gb, c, s, kernel, part); break;
-      case 3: kde1d_f32_pass<3>(xw, n, eg, G, gb, c, s, kernel, part); break;
-      case 4: kde1d_f32_pass<4>(xw, n, eg, G, gb, c, s, kernel, part); break;
-      case 5: kde1d_f32_pass<5>(xw, n, eg, G, gb, c, s, kernel, part); break;
-      case 6: kde1d_f32_pass<6>(xw, n, eg, G, gb, c, s, kernel, part); break;
-      case 7: kde1d_f32_pass<7>(xw, n, eg, G, gb, c, s, kernel, part); break;
-      default: kde1d_f32_pass<8>(xw, n, eg, G, gb, c, s, kernel, part); break;
-    }
-  }
-  __syncthreads();
-  for (int g = threadIdx.x; g < G; g += NUM_THREADS) {
-    double acc = 0.0;
-#pragma unroll
-    for (int w = 0; w < NUM_WARPS; ++w) acc += (double)part[w * G + g];
-    dens[g] = acc * scale;
-  }
-}
-
 // One entry for both arithmetic modes.  x/w: fp64 data set (n entries); in fp32 mode it is converted
 // into `xw` (which may alias x: element j of xw overlays element j of x) and the pair sums run in
 // fp32.  dens[g] = scale_pdf * sum_j (w_j/W) K((eg[g]-x_j)/bw) / bw, K including its normalisation.
@@ -195,7 +115,7 @@ __device__ __forceinline__ void kde1d_any(int fp_mode, double* x, const double* 
     xw[j] = make_float2((float)((xv - c) * s), (float)(wv * invW));
   }
   __syncthreads();
-  kde1d_f32(xw, n, eg, G, c, s, kernel, scale_pdf * knorm / bw, part, dens);
+  kde1d_f32<NUM_WARPS>(xw, n, eg, G, c, s, kernel, scale_pdf * knorm / bw, part, dens);
 }
 
 // ------------------------------------------------------------------------------------------

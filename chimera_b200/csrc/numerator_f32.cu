@@ -1,0 +1,516 @@
+// numerator_f32.cu -- fast path of the fused per-(event, hyper-point) numerator (CHB_FP32 mode).
+//
+// Same stages and semantics as numerator.cu (stage 1 reweighting, stage 2 KDE, stage 3 z-integral;
+// likelihood.py:105-301), organised for throughput on B200:
+//   * 256-thread CTAs with <= 113 KB of shared memory each, so TWO CTAs share an SM and the
+//     latency-bound phases of one (table staging, reweighting, statistics) overlap the MUFU-bound
+//     KDE pair sums of the other;
+//   * samples staged as float2 {z, w} (8 B) and rescaled in place for the pair sums;
+//   * only the tables the reweighting needs are staged (dl4 | cd4 | lut, 42 KB, one TMA bulk copy);
+//     the 300 z-grid look-ups read zi4 from L2;
+//   * one fused block reduction for all sample statistics (single pass, fp64 accumulation);
+//   * z-grid terms (E, dVc/dz, ddL/dz, psi) in fp32 on the MUFU/FP32 pipes, one division per grid
+//     point; integration weights folded into ck[k] = psi/(1+z) * trapz_w / jacobian.
+// fp64 is kept for: table construction, sample statistics, bandwidth, centring/scaling of samples
+// and grid points before the fp32 cast, cross-warp accumulation, interpolation, the z-integral and
+// the final reduction.
+#include "common.cuh"
+#include "models_f32.cuh"
+#include "kde_f32.cuh"
+#include "stage.cuh"
+
+#define F_NT 256
+#define F_NW (F_NT / 32)
+
+struct FPlan {
+  int tab, zgrid, dV, ck, pgw, eg, dens, bc, bs, xwb, part, red, stage, total;
+};
+__host__ __device__ inline FPlan make_fplan(int tab_doubles, int Nz, int B, int Ns, int kind) {
+  FPlan p;
+  int o = 0;
+  p.tab = o; o += tab_doubles;
+  p.zgrid = o; o += Nz;
+  p.dV = o; o += Nz;
+  p.ck = o; o += Nz;
+  p.pgw = o; o += Nz;
+  p.eg = o; o += Nz;
+  p.dens = o; o += Nz;
+  p.bc = o; o += B;
+  p.bs = o; o += B;
+  p.xwb = o; o += B;
+  p.part = o; o += (F_NW * Nz + 1) / 2;
+  p.red = o; o += 64;
+  o = (o + 1) & ~1;
+  p.stage = o; o += (kind == CHB_PGW_FULL ? 3 : 1) * Ns;     // float2 {z,w} [+ float4 whitened]
+  p.total = o;
+  return p;
+}
+static inline int f32_tab_doubles(const TableLayout& lay) { return lay.f32_total() - lay.f32_dl4(); }
+
+size_t numerator_f32_smem_bytes(const NumArgs& a) {
+  return (size_t)make_fplan(f32_tab_doubles(a.mc.lay), a.Nz, a.binning ? a.num_bins : 0, a.Ns, a.kind).total * sizeof(double);
+}
+
+__device__ __forceinline__ double nan_to_num_log_f(double like) {
+  double l = log(like);                  // likelihood.py:296-297
+  if (isnan(l)) return -INFINITY;
+  if (isinf(l)) return l > 0 ? CHB_DBL_MAX : -CHB_DBL_MAX;
+  return l;
+}
+
+// sum of 4 doubles + min/max of a float over the CTA in one barrier pair; result in all threads
+struct Stats6 { double a, b, c, d; float mn, mx; };
+__device__ __forceinline__ Stats6 block_stats(Stats6 v, double* red /* >= 6*F_NW doubles */) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    v.a += __shfl_xor_sync(0xffffffffu, v.a, o);
+    v.b += __shfl_xor_sync(0xffffffffu, v.b, o);
+    v.c += __shfl_xor_sync(0xffffffffu, v.c, o);
+    v.d += __shfl_xor_sync(0xffffffffu, v.d, o);
+    v.mn = fminf(v.mn, __shfl_xor_sync(0xffffffffu, v.mn, o));
+    v.mx = fmaxf(v.mx, __shfl_xor_sync(0xffffffffu, v.mx, o));
+  }
+  __syncthreads();
+  if (lane == 0) {
+    red[w * 6 + 0] = v.a; red[w * 6 + 1] = v.b; red[w * 6 + 2] = v.c; red[w * 6 + 3] = v.d;
+    red[w * 6 + 4] = (double)v.mn; red[w * 6 + 5] = (double)v.mx;
+  }
+  __syncthreads();
+  Stats6 r = {0.0, 0.0, 0.0, 0.0, INFINITY, -INFINITY};
+#pragma unroll
+  for (int i = 0; i < F_NW; ++i) {
+    r.a += red[i * 6 + 0]; r.b += red[i * 6 + 1]; r.c += red[i * 6 + 2]; r.d += red[i * 6 + 3];
+    r.mn = fminf(r.mn, (float)red[i * 6 + 4]); r.mx = fmaxf(r.mx, (float)red[i * 6 + 5]);
+  }
+  return r;
+}
+
+// rescale a float2 {x, w} data set in place to {(x - c) s, w / W} and run the fp32 pair sums
+__device__ __forceinline__ void kde_inplace(float2* xw, int n, const double* __restrict__ eg, int G, double bw, double W,
+                                            int kernel, double scale_pdf, float* part, double* dens) {
+  const double c = 0.5 * (eg[0] + eg[G - 1]);
+  const double s = (kernel == CHB_KERNEL_GAUSS) ? 0.8493218002880191 / bw : 1.0 / bw;   // sqrt(log2(e)/2)
+  const double knorm = (kernel == CHB_KERNEL_GAUSS) ? 0.3989422804014327 : 0.75;
+  const double invW = 1.0 / W;
+  for (int j = threadIdx.x; j < n; j += F_NT) {
+    const float2 v = xw[j];
+    xw[j] = make_float2((float)(((double)v.x - c) * s), (float)((double)v.y * invW));
+  }
+  __syncthreads();
+  kde1d_f32<F_NW>(xw, n, eg, G, c, s, kernel, scale_pdf * knorm / bw, part, dens);
+}
+
+#define FPHASE(i) do { if (a.prof && tid == 0) { long long _t = clock64(); pacc[i] += (unsigned long long)(_t - tlast); tlast = _t; } } while (0)
+
+__global__ void __launch_bounds__(F_NT, 2)
+numerator_f32_kernel(const NumArgs a) {
+  extern __shared__ __align__(16) double sm[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ double P[CHB_NPAR];
+  __shared__ double HC[CHB_NHC];
+  __shared__ double L[8];
+
+  const TableLayout lay = a.mc.lay;
+  const int Ns = a.Ns, Nz = a.Nz, Pp = a.P, B = a.binning ? a.num_bins : 0;
+  const int tabd = lay.f32_total() - lay.f32_dl4();
+  const FPlan pl = make_fplan(tabd, Nz, B, Ns, a.kind);
+  double* tab = sm + pl.tab;
+  double* zgrid = sm + pl.zgrid;
+  double* dV = sm + pl.dV;
+  double* ck = sm + pl.ck;
+  double* pgw = sm + pl.pgw;
+  double* eg = sm + pl.eg;
+  double* dens = sm + pl.dens;
+  double* bc = sm + pl.bc;
+  double* bs = sm + pl.bs;
+  float2* xwb = reinterpret_cast<float2*>(sm + pl.xwb);
+  float* part = reinterpret_cast<float*>(sm + pl.part);
+  double* red = sm + pl.red;
+  float2* zw = reinterpret_cast<float2*>(sm + pl.stage);
+  float4* yw = reinterpret_cast<float4*>(sm + pl.stage + Ns);      // 'full' only
+
+  const int cm = a.mc.cosmo_model;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t tab_bytes = (uint32_t)(tabd * sizeof(double));
+  const bool pixelated = (a.kind != CHB_PGW_1D);
+  const bool has_cat = (a.mc.catalog_kind == 1);
+
+  if (tid == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  uint32_t phase = 0;
+  unsigned long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tlast = clock64();
+
+  const long long units = (long long)a.Nev * a.n_hyper;
+  for (long long unit = blockIdx.x; unit < units; unit += gridDim.x) {
+    const int ev = (int)(unit / a.n_hyper), h = (int)(unit % a.n_hyper);
+    __syncthreads();
+    const double* tblk = a.tabs + (size_t)h * lay.total() + lay.off_f32();
+    if (tid == 0) {
+      fence_proxy_async();
+      mbar_expect_tx(&bar, tab_bytes);
+      bulk_g2s(tab, tblk + lay.f32_dl4(), tab_bytes, &bar);
+    }
+    if (tid < CHB_NPAR) P[tid] = a.hyper[(size_t)h * CHB_NPAR + tid];
+    if (tid >= 64 && tid < 64 + CHB_NHC) HC[tid - 64] = a.HC[(size_t)h * CHB_NHC + tid - 64];
+    const double* zgr = a.zgrids + (size_t)ev * Nz;
+    for (int k = tid; k < Nz; k += F_NT) zgrid[k] = zgr[k];
+    __syncthreads();
+
+    // constants of the fast path; table pointers: dl4|cd4|lut in shared memory, zi4 in L2
+    F32Consts fc = make_f32_consts(a.mc, P, HC, tab - lay.f32_dl4());
+    fc.zi4 = reinterpret_cast<const float4*>(tblk + lay.f32_zi4());
+    const CosmoRateF32 cr = make_cosmo_rate_f32(a.mc, P, HC);
+    const float z_top = (float)P[CHB_P_ZMAX];
+
+    // ---- z-grid terms (do not need the staged tables: overlaps the TMA copy) -------------------
+    for (int k = tid; k < Nz; k += F_NT) {
+      const double z = zgrid[k];
+      const float zf = (float)z, opz = 1.f + zf, lz = lg2f_(opz);
+      const double dCt = dCt_from_dCr(P, HC, HC[HC_DH] * (double)iinv_at_z_f32(fc, zf));
+      const float Ez = E_at_z_f32(cr, zf, opz, lz);
+      const float dHE = cr.dH * rcpf_(Ez);
+      float Xi = 1.f;
+      float ddL = (float)dCt + dHE * opz;                                   // cosmo.py:212-221
+      if (cm == CHB_COSMO_MG_FLRW) {                                         // cosmo.py:245-257
+        Xi = cr.Xi0 + (1.f - cr.Xi0) * ex2f_(-cr.n * lz);
+        ddL = ddL * Xi + ((float)dCt * opz) * (cr.n * (cr.Xi0 - 1.f) * ex2f_(-(cr.n + 1.f) * lz));
+      }
+      const double zl = (k > 0) ? zgrid[k - 1] : z, zr = (k < Nz - 1) ? zgrid[k + 1] : z;
+      dV[k] = 12.566370614359172 * (double)dHE * dCt * dCt;                  // dVc/dz
+      // psi/(1+z) * trapezoid weight / (ddL/dz (1+z)^2)
+      ck[k] = (double)(merger_rate_f32(cr, zf, lz) * rcpf_(opz) * rcpf_(ddL * opz * opz)) * (0.5 * (zr - zl));
+    }
+    FPHASE(1);
+    mbar_wait(&bar, phase);
+    phase ^= 1;
+    FPHASE(0);
+
+    // ---- stage 1: reweighting (pop_wrapper.py:67-80) ------------------------------------------
+    const size_t so = (size_t)ev * Ns;
+    Stats6 st = {0.0, 0.0, 0.0, 0.0, INFINITY, -INFINITY};
+    {
+      const float4* s4 = a.s4 + so;
+      const float2* l2 = a.l2 + so;
+#pragma unroll 2
+      for (int j = tid; j < Ns; j += F_NT) {
+        const float4 sv = __ldg(s4 + j);
+        const float2 lv = __ldg(l2 + j);
+        int b = (int)(__float_as_uint(sv.x) >> CHB_LUT_SHIFT) - (int)fc.b0;
+        b = max(0, min(b, fc.nb - 1));
+        int k = fc.lut[b];
+        float4 e = fc.dl4[k];
+        while (sv.x >= e.w && k < fc.rc - 2) { ++k; e = fc.dl4[k]; }
+        float zf = fmaf(sv.x - e.x, e.z, e.y);
+        if (sv.x >= e.w) zf = z_top;
+        if (sv.x <= 0.f) zf = 0.f;
+        const float opz = 1.f + zf;
+        const float r = rcpf_(opz), lz = lg2f_(opz);
+        const float wf = weight_f32(fc, sv.y * r, sv.z * r, lv.x - lz, lv.y - lz, sv.w);
+        zw[j] = make_float2(zf, wf);
+        const double z = (double)zf, w = (double)wf;
+        st.a += w; st.b += w * w; st.c += z; st.d += z * z;
+        st.mn = fminf(st.mn, zf); st.mx = fmaxf(st.mx, zf);
+      }
+    }
+    FPHASE(2);
+    st = block_stats(st, red);
+    const double s1 = st.a, s2 = st.b;
+    const double zmn = (double)st.mn, zmx = (double)st.mx;
+    const double zmean = st.c / Ns;
+    const double zstd = sqrt(fmax(st.d / Ns - zmean * zmean, 0.0));      // one-pass variance in fp64
+    const double norm = s1 / Ns;                  // likelihood.py:111
+    const double neff = s1 * s1 / s2;             // likelihood.py:112
+    const bool ok = (a.kind == CHB_PGW_FULL) ? !(neff < a.pe_neff) : (neff >= a.pe_neff);
+
+    double* pout = nullptr;
+    if (a.p_gw_out) pout = a.p_gw_out + ((size_t)h * a.Nev + ev) * (size_t)(pixelated ? Pp : 1) * Nz;
+    const int npix = pixelated ? a.neff_pix[ev] : 1;
+
+    if (!ok) {
+      if (pout) for (int i = tid; i < (pixelated ? Pp : 1) * Nz; i += F_NT) pout[i] = 0.0;
+      if (tid == 0) { a.log_like[(size_t)h * a.Nev + ev] = nan_to_num_log_f(0.0); a.like_raw[(size_t)h * a.Nev + ev] = 0.0; }
+      continue;
+    }
+
+    // ---- effective grid (likelihood.py:115-123 / 186-190) ------------------------------------
+    int G = Nz;
+    if (a.kind != CHB_PGW_FULL) {
+      if (a.use_cut) {
+        G = Nz / 2;
+        const double lb = (zmn - a.cut_grid * zstd > 0.0) ? zmn - a.cut_grid * zstd : 1.e-8;
+        const double ub = zmx + a.cut_grid * zstd;
+        const double step = (ub - lb) / (double)(G - 1);
+        for (int i = tid; i < G; i += F_NT) eg[i] = (i == G - 1) ? ub : __dadd_rn(__dmul_rn((double)i, step), lb);
+      } else {
+        for (int i = tid; i < G; i += F_NT) eg[i] = zgrid[i];
+      }
+    }
+    __syncthreads();
+    FPHASE(3);
+
+    double like_acc = 0.0;
+    const double fR = HC[HC_FR];
+    const double* pcat_ev = has_cat ? a.p_cat + (size_t)ev * Pp * Nz : nullptr;
+    const double* pcompl_ev = has_cat ? a.P_compl + (size_t)ev * Nz : nullptr;
+
+    if (a.kind == CHB_PGW_1D || a.kind == CHB_PGW_APPROX) {
+      float2* dxw = zw;
+      int dn = Ns;
+      double W = s1, Q = s2, dstd = zstd;
+      if (a.binning) {                           // utils/math.py:32-46
+        const double step = (zmx - zmn) / (double)B;
+        for (int i = tid; i < B; i += F_NT) {
+          double e0 = __dadd_rn(__dmul_rn((double)i, step), zmn);
+          double e1 = (i + 1 == B) ? zmx : __dadd_rn(__dmul_rn((double)(i + 1), step), zmn);
+          bc[i] = (e0 + e1) / 2;
+          bs[i] = 0.0;
+        }
+        __syncthreads();
+        for (int j = tid; j < Ns; j += F_NT) {
+          const float2 v = zw[j];
+          double f = floor(((double)v.x - zmn) / (zmx - zmn) * B);
+          if (!isnan(f)) atomicAdd(&bs[(int)fmin(fmax(f, 0.0), (double)(B - 1))], (double)v.y);
+        }
+        __syncthreads();
+        Stats6 t = {0.0, 0.0, 0.0, 0.0, 0.f, 0.f};
+        for (int i = tid; i < B; i += F_NT) { t.a += bs[i]; t.b += bs[i] * bs[i]; t.c += bc[i]; t.d += bc[i] * bc[i]; }
+        t = block_stats(t, red);
+        W = t.a; Q = t.b;
+        const double cmean = t.c / B;
+        dstd = sqrt(fmax(t.d / B - cmean * cmean, 0.0));
+        for (int i = tid; i < B; i += F_NT) xwb[i] = make_float2((float)bc[i], (float)bs[i]);
+        // (bin centres are O(1) numbers: the float cast before centring costs 6e-8 relative, like z itself)
+        dxw = xwb; dn = B;
+        __syncthreads();
+      }
+      const double neff_k = 1.0 / (Q / (W * W));
+      double bw;
+      if (a.bw_method == CHB_BW_SCOTT) bw = pow(neff_k, -0.2) * dstd;
+      else if (a.bw_method == CHB_BW_SILVERMAN) bw = pow(neff_k * 3.0 / 4.0, -0.2) * dstd;
+      else bw = a.bw_value * dstd;
+      kde_inplace(dxw, dn, eg, G, bw, W, a.kernel, norm, part, dens);
+      __syncthreads();
+      for (int k = tid; k < Nz; k += F_NT) pgw[k] = interp_lr(zgrid[k], eg, dens, G, 0.0, 0.0);
+      __syncthreads();
+      if (a.kind == CHB_PGW_1D) {
+        for (int k = tid; k < Nz; k += F_NT) {
+          like_acc += pgw[k] * dV[k] * ck[k];
+          if (pout) pout[k] = pgw[k];
+        }
+      } else {
+        const double* gwp = a.gw_pdf + (size_t)ev * Pp;
+        if (pout) for (int i = tid; i < Pp * Nz; i += F_NT) pout[i] = pgw[i % Nz] * gwp[i / Nz];
+        if (a.catA) {
+          const double* A = a.catA + (size_t)ev * Nz;
+          const double* Bk = a.catB + (size_t)ev * Nz;
+          for (int k = tid; k < Nz; k += F_NT) {
+            const double pgs = has_cat ? fR * A[k] + (1.0 - pcompl_ev[k]) * dV[k] * Bk[k] : dV[k] * Bk[k];
+            like_acc += pgw[k] * pgs * ck[k];
+          }
+        } else {
+          for (int i = tid; i < npix * Nz; i += F_NT) {
+            const int p = i / Nz, k = i - p * Nz;
+            const double pc = has_cat ? pcat_ev[(size_t)p * Nz + k] : 0.0;
+            if (pc == -100.0) continue;
+            const double pgal = has_cat ? fR * pc + (1.0 - pcompl_ev[k]) * dV[k] : dV[k];
+            like_acc += (pgw[k] * gwp[p]) * pgal * ck[k];
+          }
+        }
+      }
+    } else if (a.kind == CHB_PGW_MARG) {
+      // ---- p_gw3dmarg: per pixel, always Epanechnikov (likelihood.py:160-205) -----------------
+      const int* off = a.pix_off + (size_t)ev * (Pp + 2);
+      const double* gwp = a.gw_pdf + (size_t)ev * Pp;
+      if (pout) for (int i = tid; i < Pp * Nz; i += F_NT) pout[i] = 0.0;
+      for (int p = 0; p < npix; ++p) {
+        const int o0 = off[p], o1 = off[p + 1], nin = o1 - o0;
+        Stats6 t = {0.0, 0.0, 0.0, 0.0, INFINITY, -INFINITY};
+        for (int j = o0 + tid; j < o1; j += F_NT) {
+          const float2 v = zw[j];
+          const double z = (double)v.x, w = (double)v.y;
+          t.a += w; t.b += w * w; t.c += z; t.d += z * z; t.mx = fmaxf(t.mx, v.x);
+        }
+        t = block_stats(t, red);
+        double W = t.a, Q = t.b;
+        const double zmax_in = fmax((double)t.mx, zmn);
+        float2* dxw = zw + o0;
+        int dn = nin;
+        double dstd;
+        if (a.binning) {
+          const double step = (zmax_in - zmn) / (double)B;
+          for (int i = tid; i < B; i += F_NT) {
+            double e0 = __dadd_rn(__dmul_rn((double)i, step), zmn);
+            double e1 = (i + 1 == B) ? zmax_in : __dadd_rn(__dmul_rn((double)(i + 1), step), zmn);
+            bc[i] = (e0 + e1) / 2;
+            bs[i] = 0.0;
+          }
+          __syncthreads();
+          for (int j = o0 + tid; j < o1; j += F_NT) {
+            const float2 v = zw[j];
+            double f = floor(((double)v.x - zmn) / (zmax_in - zmn) * B);
+            if (!isnan(f)) atomicAdd(&bs[(int)fmin(fmax(f, 0.0), (double)(B - 1))], (double)v.y);
+          }
+          __syncthreads();
+          Stats6 u = {0.0, 0.0, 0.0, 0.0, 0.f, 0.f};
+          for (int i = tid; i < B; i += F_NT) { u.a += bs[i]; u.b += bs[i] * bs[i]; u.c += bc[i]; u.d += bc[i] * bc[i]; }
+          u = block_stats(u, red);
+          W = u.a; Q = u.b;
+          const double cmean = u.c / B;
+          dstd = sqrt(fmax(u.d / B - cmean * cmean, 0.0));
+          for (int i = tid; i < B; i += F_NT) xwb[i] = make_float2((float)bc[i], (float)bs[i]);
+          dxw = xwb; dn = B;
+          __syncthreads();
+        } else {
+          // std of the masked data set: in-pixel samples + (Ns - nin) copies of min(z)
+          const double nout = (double)(Ns - nin);
+          const double mm_ = (t.c + nout * zmn) / Ns;
+          const double ex2_ = (t.d + nout * zmn * zmn) / Ns;
+          dstd = sqrt(fmax(ex2_ - mm_ * mm_, 0.0));
+        }
+        const double neff_k = 1.0 / (Q / (W * W));
+        double bw;
+        if (a.bw_method == CHB_BW_SCOTT) bw = pow(neff_k, -0.2) * dstd;
+        else if (a.bw_method == CHB_BW_SILVERMAN) bw = pow(neff_k * 3.0 / 4.0, -0.2) * dstd;
+        else bw = a.bw_value * dstd;
+        const double scale = (W != 0.0) ? (norm * gwp[p]) : nan("");
+        kde_inplace(dxw, dn, eg, G, bw, W, CHB_KERNEL_EPAN, 1.0, part, dens);
+        __syncthreads();
+        for (int k = tid; k < Nz; k += F_NT) {
+          const double raw = interp_lr(zgrid[k], eg, dens, G, 0.0, 0.0);
+          const bool inside = (zgrid[k] >= eg[0] && zgrid[k] <= eg[G - 1]);
+          const double v = inside ? raw * scale : 0.0;
+          const double pc = has_cat ? pcat_ev[(size_t)p * Nz + k] : 0.0;
+          if (pout) pout[(size_t)p * Nz + k] = v;
+          if (pc == -100.0) continue;
+          const double pgal = has_cat ? fR * pc + (1.0 - pcompl_ev[k]) * dV[k] : dV[k];
+          like_acc += v * pgal * ck[k];
+        }
+        __syncthreads();
+      }
+    } else {
+      // ---- p_gw3dfull: 3-D whitened Gaussian KDE (likelihood.py:211-260, math.py:154-229) ------
+      const double* ra = a.ra + so;
+      const double* dec = a.dec + so;
+      const double W = s1;
+      const double Qn = s2 / (W * W);
+      const double neff_k = 1.0 / Qn;
+      double factor;
+      if (a.bw_method == CHB_BW_SCOTT) factor = pow(neff_k, -1.0 / 7.0);
+      else if (a.bw_method == CHB_BW_SILVERMAN) factor = pow(neff_k * 5.0 / 4.0, -1.0 / 7.0);
+      else factor = a.bw_value;
+      double m0 = 0, m1 = 0, m2 = 0;
+      for (int j = tid; j < Ns; j += F_NT) { const float2 v = zw[j]; double wn = (double)v.y / W; m0 += wn * (double)v.x; m1 += wn * ra[j]; m2 += wn * dec[j]; }
+      m0 = block_sum(m0, red); m1 = block_sum(m1, red); m2 = block_sum(m2, red);
+      double c00 = 0, c01 = 0, c02 = 0, c11 = 0, c12 = 0, c22 = 0;
+      for (int j = tid; j < Ns; j += F_NT) {
+        const float2 v = zw[j];
+        double wn = (double)v.y / W, r0 = (double)v.x - m0, r1 = ra[j] - m1, r2 = dec[j] - m2;
+        c00 += wn * r0 * r0; c01 += wn * r0 * r1; c02 += wn * r0 * r2;
+        c11 += wn * r1 * r1; c12 += wn * r1 * r2; c22 += wn * r2 * r2;
+      }
+      c00 = block_sum(c00, red); c01 = block_sum(c01, red); c02 = block_sum(c02, red);
+      c11 = block_sum(c11, red); c12 = block_sum(c12, red); c22 = block_sum(c22, red);
+      if (tid == 0) {
+        const double dn_ = 1.0 - Qn;
+        c00 /= dn_; c01 /= dn_; c02 /= dn_; c11 /= dn_; c12 /= dn_; c22 /= dn_;
+        const double a00 = c11 * c22 - c12 * c12, a01 = c02 * c12 - c01 * c22, a02 = c01 * c12 - c02 * c11;
+        const double a11 = c00 * c22 - c02 * c02, a12 = c01 * c02 - c00 * c12, a22 = c00 * c11 - c01 * c01;
+        const double det = c00 * a00 + c01 * a01 + c02 * a02;
+        const double f2 = factor * factor;
+        const double i00 = a00 / det / f2, i01 = a01 / det / f2, i02 = a02 / det / f2;
+        const double i11 = a11 / det / f2, i12 = a12 / det / f2, i22 = a22 / det / f2;
+        const double l00 = sqrt(i00), l10 = i01 / l00, l20 = i02 / l00;
+        const double l11 = sqrt(i11 - l10 * l10), l21 = (i12 - l20 * l10) / l11;
+        const double l22 = sqrt(i22 - l20 * l20 - l21 * l21);
+        L[0] = l00; L[1] = l10; L[2] = l11; L[3] = l20; L[4] = l21; L[5] = l22;
+        L[6] = log(l00) + log(l11) + log(l22) - 1.5 * log(2.0 * CHB_PI);
+      }
+      __syncthreads();
+      const double l00 = L[0], l10 = L[1], l11 = L[2], l20 = L[3], l21 = L[4], l22 = L[5], lognorm = L[6];
+      const double ps = 0.8493218002880191;            // sqrt(log2(e)/2)
+      for (int j = tid; j < Ns; j += F_NT) {
+        const float2 v = zw[j];
+        const double r0 = (double)v.x - m0, r1 = ra[j] - m1, r2 = dec[j] - m2;
+        yw[j] = make_float4((float)((r0 * l00 + r1 * l10 + r2 * l20) * ps), (float)((r1 * l11 + r2 * l21) * ps),
+                            (float)((r2 * l22) * ps), (float)((double)v.y / W));
+      }
+      if (pout) for (int i = tid; i < Pp * Nz; i += F_NT) pout[i] = 0.0;
+      const double zlo = zmn - a.cut_grid * zstd, zhi = zmx + a.cut_grid * zstd;   // likelihood.py:225
+      int* kmask = reinterpret_cast<int*>(dens);
+      if (tid == 0) {
+        int c = 0;
+        for (int k = 0; k < Nz; ++k) if (zgrid[k] <= zhi && zgrid[k] >= zlo) kmask[c++] = k;
+        L[7] = (double)c;
+      }
+      __syncthreads();
+      const int nmask = (int)L[7];
+      const double* rap = a.ra_pix + (size_t)ev * Pp;
+      const double* dep = a.dec_pix + (size_t)ev * Pp;
+      const int npts = npix * nmask;
+      constexpr int FR = 2;
+      const double enorm = exp(lognorm) * norm;
+      const int ntiles = (npts + 32 * FR - 1) / (32 * FR);
+      for (int t = warp; t < ntiles; t += F_NW) {
+        float q0[FR], q1[FR], q2[FR], acc[FR];
+        int pk[FR];
+#pragma unroll
+        for (int r = 0; r < FR; ++r) {
+          const int i = t * 32 * FR + r * 32 + lane;
+          pk[r] = -1; acc[r] = 0.f;
+          q0[r] = q1[r] = q2[r] = 1.0e18f;
+          if (i < npts) {
+            const int p = i / nmask, k = kmask[i - p * nmask];
+            pk[r] = p * Nz + k;
+            const double r0 = zgrid[k] - m0, r1 = rap[p] - m1, r2 = dep[p] - m2;
+            q0[r] = (float)((r0 * l00 + r1 * l10 + r2 * l20) * ps);
+            q1[r] = (float)((r1 * l11 + r2 * l21) * ps);
+            q2[r] = (float)((r2 * l22) * ps);
+          }
+        }
+#pragma unroll 4
+        for (int j = 0; j < Ns; ++j) {
+          const float4 v = yw[j];
+#pragma unroll
+          for (int r = 0; r < FR; ++r) {
+            const float d0 = v.x - q0[r], d1 = v.y - q1[r], d2 = v.z - q2[r];
+            const float e = fmaf(d2, d2, fmaf(d1, d1, d0 * d0));
+            acc[r] = fmaf(v.w, ex2_ftz(-e), acc[r]);
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < FR; ++r) {
+          if (pk[r] < 0) continue;
+          const int p = pk[r] / Nz, k = pk[r] - p * Nz;
+          const double v = (double)acc[r] * enorm;
+          if (pout) pout[(size_t)p * Nz + k] = v;
+          const double pc = has_cat ? pcat_ev[(size_t)p * Nz + k] : 0.0;
+          if (pc != -100.0) {
+            const double pgal = has_cat ? fR * pc + (1.0 - pcompl_ev[k]) * dV[k] : dV[k];
+            like_acc += v * pgal * ck[k];
+          }
+        }
+      }
+    }
+
+    FPHASE(4);
+    const double like = block_sum(like_acc, red);
+    if (tid == 0) { a.log_like[(size_t)h * a.Nev + ev] = nan_to_num_log_f(like); a.like_raw[(size_t)h * a.Nev + ev] = like; }
+    FPHASE(5);
+  }
+  if (a.prof && tid == 0) for (int i = 0; i < 8; ++i) a.prof[(size_t)blockIdx.x * 8 + i] = pacc[i];
+}
+
+cudaError_t numerator_f32_configure(size_t smem) {
+  return cudaFuncSetAttribute(numerator_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+int numerator_f32_ctas_per_sm(size_t smem) {
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, numerator_f32_kernel, F_NT, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+cudaError_t launch_numerator_f32(const NumArgs& a, int grid, size_t smem, cudaStream_t s) {
+  numerator_f32_kernel<<<grid, F_NT, smem, s>>>(a);
+  return cudaGetLastError();
+}
