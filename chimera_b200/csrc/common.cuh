@@ -14,6 +14,7 @@ struct NumArgs {
   ModelCfg mc;
   // hyperlikelihood options (likelihood.py:48-62)
   int kind, kernel, bw_method, use_cut, binning, num_bins, fp_mode;
+  int rec_off;           // 1: disable the Gaussian recurrence (one MUFU.EX2 per pair), env CHB_KDE_DIRECT=1
   double bw_value, cut_grid, pe_neff;
   // event data, samples permuted so that each pixel's samples are contiguous
   int Nev, Ns, Nz, P;

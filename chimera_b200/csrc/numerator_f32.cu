@@ -87,8 +87,10 @@ __device__ __forceinline__ Stats6 block_stats(Stats6 v, double* red /* >= 6*F_NW
 }
 
 // rescale a float2 {x, w} data set in place to {(x - c) s, w / W} and run the fp32 pair sums
+// `ustep` > 0: eg is a uniform grid with that spacing -> Gaussian sums by recurrence when the scaled
+// spacing allows it (kde_f32.cuh).
 __device__ __forceinline__ void kde_inplace(float2* xw, int n, const double* __restrict__ eg, int G, double bw, double W,
-                                            int kernel, double scale_pdf, float* part, double* dens) {
+                                            int kernel, double scale_pdf, float* part, double* dens, double ustep = 0.0) {
   const double c = 0.5 * (eg[0] + eg[G - 1]);
   const double s = (kernel == CHB_KERNEL_GAUSS) ? 0.8493218002880191 / bw : 1.0 / bw;   // sqrt(log2(e)/2)
   const double knorm = (kernel == CHB_KERNEL_GAUSS) ? 0.3989422804014327 : 0.75;
@@ -98,7 +100,10 @@ __device__ __forceinline__ void kde_inplace(float2* xw, int n, const double* __r
     xw[j] = make_float2((float)(((double)v.x - c) * s), (float)((double)v.y * invW));
   }
   __syncthreads();
-  kde1d_f32<F_NW>(xw, n, eg, G, c, s, kernel, scale_pdf * knorm / bw, part, dens);
+  if (kernel == CHB_KERNEL_GAUSS && ustep > 0.0 && ustep * s <= 1.0 && G >= 2)
+    kde1d_f32_rec<F_NW>(xw, n, eg, G, c, s, ustep, scale_pdf * knorm / bw, part, dens);
+  else
+    kde1d_f32<F_NW>(xw, n, eg, G, c, s, kernel, scale_pdf * knorm / bw, part, dens);
 }
 
 #define FPHASE(i) do { if (a.prof && tid == 0) { long long _t = clock64(); pacc[i] += (unsigned long long)(_t - tlast); tlast = _t; } } while (0)
@@ -236,12 +241,14 @@ numerator_f32_kernel(const NumArgs a) {
 
     // ---- effective grid (likelihood.py:115-123 / 186-190) ------------------------------------
     int G = Nz;
+    double ustep = 0.0;       // spacing of the effective grid when it is our own linspace
     if (a.kind != CHB_PGW_FULL) {
       if (a.use_cut) {
         G = Nz / 2;
         const double lb = (zmn - a.cut_grid * zstd > 0.0) ? zmn - a.cut_grid * zstd : 1.e-8;
         const double ub = zmx + a.cut_grid * zstd;
         const double step = (ub - lb) / (double)(G - 1);
+        ustep = a.rec_off ? 0.0 : step;
         for (int i = tid; i < G; i += F_NT) eg[i] = (i == G - 1) ? ub : __dadd_rn(__dmul_rn((double)i, step), lb);
       } else {
         for (int i = tid; i < G; i += F_NT) eg[i] = zgrid[i];
@@ -290,7 +297,7 @@ numerator_f32_kernel(const NumArgs a) {
       if (a.bw_method == CHB_BW_SCOTT) bw = pow(neff_k, -0.2) * dstd;
       else if (a.bw_method == CHB_BW_SILVERMAN) bw = pow(neff_k * 3.0 / 4.0, -0.2) * dstd;
       else bw = a.bw_value * dstd;
-      kde_inplace(dxw, dn, eg, G, bw, W, a.kernel, norm, part, dens);
+      kde_inplace(dxw, dn, eg, G, bw, W, a.kernel, norm, part, dens, ustep);
       __syncthreads();
       for (int k = tid; k < Nz; k += F_NT) pgw[k] = interp_lr(zgrid[k], eg, dens, G, 0.0, 0.0);
       __syncthreads();
