@@ -34,8 +34,8 @@ enum {
   HC_LG2_Z1,        // log2(z_grid_interp[1]) = log2(1e-10)
   HC_INV_LG2_ZSTEP  // (rc-2) / (log2 z_max - log2 1e-10)
 };
-#define CHB_LUT_SHIFT 19      // 16 buckets per octave of dL
-#define CHB_LUT_CAP 1024      // uint16 entries
+#define CHB_LUT_SHIFT 18      // 32 buckets per octave of dL: <= 1.4 knots per bucket, so <= 2 scan steps
+#define CHB_LUT_CAP 2048      // uint16 entries
 
 #define CHB_PI 3.141592653589793238462643383279502884
 #define CHB_DBL_MAX 1.7976931348623157e308

@@ -31,6 +31,7 @@ struct F32Consts {
   float lo, hi, neg_alpha, beta, dm, inv_norm_p1;
   float lam, mu, g_hi, g_c, g_pref, inv_plnorm;       // plp
   float mb, neg_alpha2, ratio;                          // bpl
+  float4 cd4_last;                                      // last row of cd4 (clamp)
 };
 
 __device__ __forceinline__ F32Consts make_f32_consts(const ModelCfg& mc, const double* __restrict__ P,
@@ -57,6 +58,7 @@ __device__ __forceinline__ F32Consts make_f32_consts(const ModelCfg& mc, const d
   c.g_pref = (float)(1.0 / (sg * 2.5066282746310002 * HC[HC_TG_NORM]));
   c.inv_plnorm = (float)(1.0 / HC[HC_PL_NORM]);
   c.mb = (float)HC[HC_MBREAK]; c.neg_alpha2 = (float)(-P[CHB_P_ALPHA2]); c.ratio = (float)HC[HC_BPL_RATIO];
+  c.cd4_last = make_float4((float)P[CHB_P_MHIGH], 0.f, 0.f, 0.f);   // callers with cd4 resident overwrite it
   return c;
 }
 
@@ -125,6 +127,60 @@ __device__ __forceinline__ float weight_f32(const F32Consts& c, float m1, float 
   p2 = p2 * rcpf_(cdf);
   if (p2 != p2) p2 = 0.f;                              // 0/0 -> 0 (mass.py:340)
   return p1 * c.inv_norm_p1 * p2 * inv_prior;
+}
+
+// Branch-free variants for software-pipelined loops (several samples in flight per thread): every
+// sample executes the same instruction stream, support tests become selects.
+__device__ __forceinline__ float smoothing_bf(float m, float dm, float lo) {
+  const float x = m - lo;
+  // dm/x + dm/(x-dm) = dm (2x - dm) / (x (x - dm)): one reciprocal
+  const float t = dm * (2.f * x - dm) * rcpf_(x * (x - dm));
+  float S = rcpf_(1.f + ex2f_(t * CHB_LOG2E_F));
+  S = (x > dm) ? 1.f : S;
+  return (x < 0.f) ? 0.f : S;
+}
+__device__ __forceinline__ float weight_bf(const F32Consts& c, float m1, float m2, float lg2m1, float lg2m2,
+                                           float inv_prior) {
+  const bool in1 = (c.lo <= m1) && (m1 <= c.hi);
+  float p1;
+  if (c.mass_model == CHB_MASS_TPL) {
+    p1 = ex2f_(c.neg_alpha * lg2m1);
+  } else if (c.mass_model == CHB_MASS_BPL) {
+    const float a = (m1 <= c.mb) ? ex2f_(c.neg_alpha * lg2m1) : 0.f;
+    const float b = (m1 >= c.mb) ? ex2f_(c.neg_alpha2 * lg2m1) * c.ratio : 0.f;
+    p1 = (a + b) * smoothing_bf(m1, c.dm, c.lo);
+  } else {
+    const float Ppl = ex2f_(c.neg_alpha * lg2m1) * c.inv_plnorm;
+    const float d = m1 - c.mu;
+    const float G = (m1 <= c.g_hi) ? ex2f_(c.g_c * d * d) * c.g_pref : 0.f;
+    p1 = ((1.f - c.lam) * Ppl + c.lam * G) * smoothing_bf(m1, c.dm, c.lo);
+  }
+  float p2 = ex2f_(c.beta * lg2m2);
+  if (c.mass_model != CHB_MASS_TPL) p2 *= smoothing_bf(m2, c.dm, c.lo);
+  int i = (int)((lg2m1 - c.lg2_m0) * c.inv_lg2_mstep);
+  i = max(0, min(i, c.rm - 2));
+  const float4 e = c.cd4[i];
+  float cdf = fmaf(m1 - e.x, e.z, e.y);
+  cdf = (m1 >= c.cd4_last.x) ? c.cd4_last.y : cdf;
+  p2 = p2 * rcpf_(cdf);
+  p2 = (p2 != p2) ? 0.f : p2;                          // 0/0 -> 0 (mass.py:340)
+  const bool in2 = (c.lo <= m2) && (m2 <= m1);
+  const float w = p1 * c.inv_norm_p1 * p2 * inv_prior;
+  return (in1 && in2 && p1 > 1e-25f) ? w : 0.f;
+}
+// dL -> z with a fixed two-step scan (covers every bucket of a monotone table at 32 buckets/octave);
+// `more` tells the caller that a longer scan is needed (non-monotone / unusually dense tables).
+__device__ __forceinline__ float z_lookup2(const F32Consts& c, float dL, float z_top, int& k, float4& e, bool& more) {
+  int b = (int)(__float_as_uint(dL) >> CHB_LUT_SHIFT) - (int)c.b0;
+  b = max(0, min(b, c.nb - 1));
+  k = c.lut[b];
+  e = c.dl4[k];
+  if (dL >= e.w && k < c.rc - 2) { ++k; e = c.dl4[k]; }
+  if (dL >= e.w && k < c.rc - 2) { ++k; e = c.dl4[k]; }
+  more = (dL >= e.w && k < c.rc - 2);
+  float z = fmaf(dL - e.x, e.z, e.y);
+  z = (dL >= e.w) ? z_top : z;
+  return (dL <= 0.f) ? 0.f : z;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -168,6 +168,7 @@ numerator_f32_kernel(const NumArgs a) {
     fc.zi4 = reinterpret_cast<const float4*>(tblk + lay.f32_zi4());
     const CosmoRateF32 cr = make_cosmo_rate_f32(a.mc, P, HC);
     const float z_top = (float)P[CHB_P_ZMAX];
+    // (fc.cd4_last is filled after the table copy has landed)
 
     // ---- z-grid terms (do not need the staged tables: overlaps the TMA copy) -------------------
     for (int k = tid; k < Nz; k += F_NT) {
@@ -190,33 +191,54 @@ numerator_f32_kernel(const NumArgs a) {
     FPHASE(1);
     mbar_wait(&bar, phase);
     phase ^= 1;
+    fc.cd4_last = fc.cd4[fc.rm - 1];
     FPHASE(0);
 
     // ---- stage 1: reweighting (pop_wrapper.py:67-80) ------------------------------------------
     const size_t so = (size_t)ev * Ns;
     Stats6 st = {0.0, 0.0, 0.0, 0.0, INFINITY, -INFINITY};
     {
+      // four samples in flight per thread, identical instruction stream for all of them (branch-free
+      // weights, fixed two-step table scan) so the compiler interleaves their dependency chains
       const float4* s4 = a.s4 + so;
       const float2* l2 = a.l2 + so;
-#pragma unroll 2
-      for (int j = tid; j < Ns; j += F_NT) {
-        const float4 sv = __ldg(s4 + j);
-        const float2 lv = __ldg(l2 + j);
-        int b = (int)(__float_as_uint(sv.x) >> CHB_LUT_SHIFT) - (int)fc.b0;
-        b = max(0, min(b, fc.nb - 1));
-        int k = fc.lut[b];
-        float4 e = fc.dl4[k];
-        while (sv.x >= e.w && k < fc.rc - 2) { ++k; e = fc.dl4[k]; }
-        float zf = fmaf(sv.x - e.x, e.z, e.y);
-        if (sv.x >= e.w) zf = z_top;
-        if (sv.x <= 0.f) zf = 0.f;
-        const float opz = 1.f + zf;
-        const float r = rcpf_(opz), lz = lg2f_(opz);
-        const float wf = weight_f32(fc, sv.y * r, sv.z * r, lv.x - lz, lv.y - lz, sv.w);
-        zw[j] = make_float2(zf, wf);
-        const double z = (double)zf, w = (double)wf;
-        st.a += w; st.b += w * w; st.c += z; st.d += z * z;
-        st.mn = fminf(st.mn, zf); st.mx = fmaxf(st.mx, zf);
+      constexpr int U = 4;
+      for (int jb = tid; jb < Ns; jb += U * F_NT) {
+        float4 sv[U]; float2 lv[U]; float zf[U], wf[U];
+        int kk[U]; float4 ee[U]; bool more[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int j = min(jb + u * F_NT, Ns - 1);          // tail lanes recompute the last sample, never stored
+          sv[u] = __ldg(s4 + j);
+          lv[u] = __ldg(l2 + j);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) zf[u] = z_lookup2(fc, sv[u].x, z_top, kk[u], ee[u], more[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (more[u]) {                                      // rare: keep scanning
+            int k = kk[u]; float4 e = ee[u];
+            while (sv[u].x >= e.w && k < fc.rc - 2) { ++k; e = fc.dl4[k]; }
+            float z = fmaf(sv[u].x - e.x, e.z, e.y);
+            zf[u] = (sv[u].x >= e.w) ? z_top : z;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const float opz = 1.f + zf[u];
+          const float r = rcpf_(opz), lz = lg2f_(opz);
+          wf[u] = weight_bf(fc, sv[u].y * r, sv[u].z * r, lv[u].x - lz, lv[u].y - lz, sv[u].w);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int j = jb + u * F_NT;
+          if (j < Ns) {
+            zw[j] = make_float2(zf[u], wf[u]);
+            const double z = (double)zf[u], w = (double)wf[u];
+            st.a += w; st.b += w * w; st.c += z; st.d += z * z;
+            st.mn = fminf(st.mn, zf[u]); st.mx = fmaxf(st.mx, zf[u]);
+          }
+        }
       }
     }
     FPHASE(2);

@@ -93,7 +93,8 @@ selection_f32_kernel(SelArgs a) {
   if (tid < CHB_NHC) HC[tid] = a.HC[(size_t)h * CHB_NHC + tid];
   __syncthreads();
   mbar_wait(&bar, 0);
-  const F32Consts fc = make_f32_consts(a.mc, P, HC, sm - part_off);   // zi4 (not staged) is never touched here
+  F32Consts fc = make_f32_consts(a.mc, P, HC, sm - part_off);   // zi4 (not staged) is never touched here
+  fc.cd4_last = fc.cd4[fc.rm - 1];
   const CosmoRateF32 cr = make_cosmo_rate_f32(a.mc, P, HC);
   const float z_top = (float)a.tabs[(size_t)h * lay.total() + lay.off_zg() + lay.rc - 1];
 
