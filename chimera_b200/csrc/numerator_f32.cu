@@ -90,20 +90,30 @@ __device__ __forceinline__ Stats6 block_stats(Stats6 v, double* red /* >= 6*F_NW
 // `ustep` > 0: eg is a uniform grid with that spacing -> Gaussian sums by recurrence when the scaled
 // spacing allows it (kde_f32.cuh).
 __device__ __forceinline__ void kde_inplace(float2* xw, int n, const double* __restrict__ eg, int G, double bw, double W,
-                                            int kernel, double scale_pdf, float* part, double* dens, double ustep = 0.0) {
+                                            int kernel, double scale_pdf, float* part, int part_floats, double* dens,
+                                            double ustep = 0.0) {
   const double c = 0.5 * (eg[0] + eg[G - 1]);
   const double s = (kernel == CHB_KERNEL_GAUSS) ? 0.8493218002880191 / bw : 1.0 / bw;   // sqrt(log2(e)/2)
   const double knorm = (kernel == CHB_KERNEL_GAUSS) ? 0.3989422804014327 : 0.75;
   const double invW = 1.0 / W;
-  for (int j = threadIdx.x; j < n; j += F_NT) {
-    const float2 v = xw[j];
-    xw[j] = make_float2((float)(((double)v.x - c) * s), (float)((double)v.y * invW));
-  }
-  __syncthreads();
-  if (kernel == CHB_KERNEL_GAUSS && ustep > 0.0 && ustep * s <= 1.0 && G >= 2)
-    kde1d_f32_rec<F_NW>(xw, n, eg, G, c, s, ustep, scale_pdf * knorm / bw, part, dens);
-  else
+  int R = 0, LPS = 0;
+  const float h = (float)(ustep * s);
+  const bool rec = (kernel == CHB_KERNEL_GAUSS) && ustep > 0.0 && G >= 2 && rec2_choose(G, h, part_floats, F_NW, R, LPS);
+  if (rec) {
+    for (int j = threadIdx.x; j < n; j += F_NT) {
+      const float2 v = xw[j];
+      xw[j] = make_float2((float)(((double)v.x - c) * s), lg2f_((float)((double)v.y * invW)));
+    }
+    __syncthreads();
+    kde1d_f32_rec2<F_NW>(xw, n, eg, G, c, s, h, R, LPS, scale_pdf * knorm / bw, part, dens);
+  } else {
+    for (int j = threadIdx.x; j < n; j += F_NT) {
+      const float2 v = xw[j];
+      xw[j] = make_float2((float)(((double)v.x - c) * s), (float)((double)v.y * invW));
+    }
+    __syncthreads();
     kde1d_f32<F_NW>(xw, n, eg, G, c, s, kernel, scale_pdf * knorm / bw, part, dens);
+  }
 }
 
 #define FPHASE(i) do { if (a.prof && tid == 0) { long long _t = clock64(); pacc[i] += (unsigned long long)(_t - tlast); tlast = _t; } } while (0)
@@ -319,7 +329,7 @@ numerator_f32_kernel(const NumArgs a) {
       if (a.bw_method == CHB_BW_SCOTT) bw = pow(neff_k, -0.2) * dstd;
       else if (a.bw_method == CHB_BW_SILVERMAN) bw = pow(neff_k * 3.0 / 4.0, -0.2) * dstd;
       else bw = a.bw_value * dstd;
-      kde_inplace(dxw, dn, eg, G, bw, W, a.kernel, norm, part, dens, ustep);
+      kde_inplace(dxw, dn, eg, G, bw, W, a.kernel, norm, part, F_NW * Nz, dens, ustep);
       __syncthreads();
       for (int k = tid; k < Nz; k += F_NT) pgw[k] = interp_lr(zgrid[k], eg, dens, G, 0.0, 0.0);
       __syncthreads();
@@ -404,7 +414,7 @@ numerator_f32_kernel(const NumArgs a) {
         else if (a.bw_method == CHB_BW_SILVERMAN) bw = pow(neff_k * 3.0 / 4.0, -0.2) * dstd;
         else bw = a.bw_value * dstd;
         const double scale = (W != 0.0) ? (norm * gwp[p]) : nan("");
-        kde_inplace(dxw, dn, eg, G, bw, W, CHB_KERNEL_EPAN, 1.0, part, dens);
+        kde_inplace(dxw, dn, eg, G, bw, W, CHB_KERNEL_EPAN, 1.0, part, F_NW * Nz, dens);
         __syncthreads();
         for (int k = tid; k < Nz; k += F_NT) {
           const double raw = interp_lr(zgrid[k], eg, dens, G, 0.0, 0.0);
