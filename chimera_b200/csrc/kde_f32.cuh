@@ -152,7 +152,7 @@ __device__ __forceinline__ void kde1d_f32_rec2_pass(const float2* __restrict__ x
   for (int r = 0; r < R; ++r) acc[r] = 0.f;
   const int per = (n + NW - 1) / NW;
   const int j0 = min(n, warp * per), j1 = min(n, j0 + per);
-#pragma unroll 2
+#pragma unroll 4
   for (int j = j0 + sub; j < j1; j += S) {
     const float2 v = xl[j];
     const float d = gp - v.x;

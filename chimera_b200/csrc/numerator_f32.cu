@@ -125,6 +125,7 @@ numerator_f32_kernel(const NumArgs a) {
   __shared__ double P[CHB_NPAR];
   __shared__ double HC[CHB_NHC];
   __shared__ double L[8];
+  __shared__ int next_chunk;
 
   const TableLayout lay = a.mc.lay;
   const int Ns = a.Ns, Nz = a.Nz, Pp = a.P, B = a.binning ? a.num_bins : 0;
@@ -169,6 +170,7 @@ numerator_f32_kernel(const NumArgs a) {
     }
     if (tid < CHB_NPAR) P[tid] = a.hyper[(size_t)h * CHB_NPAR + tid];
     if (tid >= 64 && tid < 64 + CHB_NHC) HC[tid - 64] = a.HC[(size_t)h * CHB_NHC + tid - 64];
+    if (tid == 128) next_chunk = 0;
     const double* zgr = a.zgrids + (size_t)ev * Nz;
     for (int k = tid; k < Nz; k += F_NT) zgrid[k] = zgr[k];
     __syncthreads();
@@ -180,8 +182,10 @@ numerator_f32_kernel(const NumArgs a) {
     const float z_top = (float)P[CHB_P_ZMAX];
     // (fc.cd4_last is filled after the table copy has landed)
 
-    // ---- z-grid terms (do not need the staged tables: overlaps the TMA copy) -------------------
-    for (int k = tid; k < Nz; k += F_NT) {
+    // ---- z-grid terms: warp 0 only, while the other warps already reweight samples (they need no
+    // staged table; results are consumed after the KDE) ----------------------------------------
+    if (warp == 0)
+    for (int k = lane; k < Nz; k += 32) {
       const double z = zgrid[k];
       const float zf = (float)z, opz = 1.f + zf, lz = lg2f_(opz);
       const double dCt = dCt_from_dCr(P, HC, HC[HC_DH] * (double)iinv_at_z_f32(fc, zf));
@@ -213,12 +217,17 @@ numerator_f32_kernel(const NumArgs a) {
       const float4* s4 = a.s4 + so;
       const float2* l2 = a.l2 + so;
       constexpr int U = 4;
-      for (int jb = tid; jb < Ns; jb += U * F_NT) {
+      for (;;) {
+        int cbase = 0;
+        if (lane == 0) cbase = atomicAdd(&next_chunk, U * 32);     // warps pull 128-sample chunks (warp 0 joins late)
+        cbase = __shfl_sync(0xffffffffu, cbase, 0);
+        if (cbase >= Ns) break;
+        const int jb = cbase + lane;
         float4 sv[U]; float2 lv[U]; float zf[U], wf[U];
         int kk[U]; float4 ee[U]; bool more[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const int j = min(jb + u * F_NT, Ns - 1);          // tail lanes recompute the last sample, never stored
+          const int j = min(jb + u * 32, Ns - 1);            // tail lanes recompute the last sample, never stored
           sv[u] = __ldg(s4 + j);
           lv[u] = __ldg(l2 + j);
         }
@@ -241,7 +250,7 @@ numerator_f32_kernel(const NumArgs a) {
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const int j = jb + u * F_NT;
+          const int j = jb + u * 32;
           if (j < Ns) {
             zw[j] = make_float2(zf[u], wf[u]);
             const double z = (double)zf[u], w = (double)wf[u];
