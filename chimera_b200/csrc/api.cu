@@ -59,6 +59,7 @@ struct chb_handle {
   DevBuf<unsigned long long> prof;
   DevBuf<float4> s4;
   DevBuf<float2> l2;
+  DevBuf<float2> zterms;
   DevBuf<double> catA, catB;
   bool cat_collapsed = false;
   bool want_prof = false;
@@ -156,7 +157,7 @@ void chb_destroy(chb_handle* h) {
   for (auto* b : dbl) b->release();
   h->pix_off.release();
   h->prof.release();
-  h->s4.release(); h->l2.release(); h->inj_s4.release(); h->inj_l2.release(); h->catA.release(); h->catB.release();
+  h->s4.release(); h->l2.release(); h->inj_s4.release(); h->inj_l2.release(); h->zterms.release(); h->catA.release(); h->catB.release();
   h->neff_pix.release();
   for (auto& evn : h->ev) if (evn) cudaEventDestroy(evn);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -384,6 +385,16 @@ static int eval_impl(chb_handle* h, int64_t n_hyper, const double* d_hyper, doub
           int grid = (int)std::min<long long>(units, (long long)h->sm_count * per_sm);
           h->num_grid = grid; h->num_smem = fs;
           if (h->want_prof) { CU(h->prof.alloc((size_t)grid * 8), "alloc profile"); a.prof = h->prof.p; }
+          // z-grid terms for all (hyper-point, event, k) in one full-occupancy pass when they fit in 2 GiB
+          const size_t zt_elems = (size_t)n_hyper * h->Nev * h->Nz;
+          a.zterms = nullptr; a.zterms_out = nullptr; a.zterms_h0 = 0;
+          if (zt_elems * sizeof(float2) <= ((size_t)2 << 30)) {
+            CU(h->zterms.alloc(zt_elems), "alloc z-grid terms");
+            a.zterms_out = h->zterms.p;
+            CU(launch_zgrid_terms(a, 0, (int)n_hyper, s), "zgrid_terms launch");
+            h->launches++;
+            a.zterms = h->zterms.p;
+          }
           CU(launch_numerator_f32(a, grid, fs, s), "numerator_f32 launch");
           fast = true;
         }

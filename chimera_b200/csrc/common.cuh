@@ -41,6 +41,10 @@ struct NumArgs {
   double* log_like;      // (n_hyper, Nev)
   double* like_raw;      // (n_hyper, Nev) integral before log / nan_to_num
   double* p_gw_out;      // optional (n_hyper, Nev, [P,] Nz)
+  // fp32 fast path: precomputed z-grid terms {dVc/dz, ck} for hyper-points [zterms_h0, zterms_h0 + n)
+  const float2* zterms;
+  float2* zterms_out;
+  int zterms_h0;
   // optional phase profile: (gridDim, 8) SM-clock cycles accumulated by thread 0 of every CTA
   unsigned long long* prof;
   // per-CTA global scratch for sample staging when it does not fit in shared memory
@@ -72,6 +76,7 @@ size_t numerator_f32_smem_bytes(const NumArgs& a);
 cudaError_t numerator_f32_configure(size_t smem);
 int numerator_f32_ctas_per_sm(size_t smem);
 cudaError_t launch_numerator_f32(const NumArgs& a, int grid, size_t smem, cudaStream_t s);
+cudaError_t launch_zgrid_terms(const NumArgs& a, int h0, int nh, cudaStream_t s);
 cudaError_t launch_catalog_collapse(int Nev, int P, int Nz, const double* p_cat, const double* gw_pdf, const int* neff_pix,
                                    double* catA, double* catB, cudaStream_t s);
 cudaError_t launch_reduce(int n_hyper, int Nev, int tiles, const double* d_log_like, const double* d_tile_part,

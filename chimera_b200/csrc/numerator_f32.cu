@@ -18,6 +18,7 @@
 #include "models_f32.cuh"
 #include "kde_f32.cuh"
 #include "stage.cuh"
+#include <algorithm>
 
 #define F_NT 256
 #define F_NW (F_NT / 32)
@@ -116,6 +117,57 @@ __device__ __forceinline__ void kde_inplace(float2* xw, int n, const double* __r
   }
 }
 
+// z-grid terms of one (hyper-point, z): {dVc/dz, psi/(1+z) * trapezoid weight / (ddL/dz (1+z)^2)}
+// (cosmo.py:188-221,245-257, rate.py:96-129, likelihood.py:272,289).  E, ddL/dz, psi in fp32; the
+// comoving distance through the packed zi4 table.
+__device__ __forceinline__ float2 zgrid_terms_f32(const F32Consts& fc, const CosmoRateF32& cr, const double* __restrict__ P,
+                                                  const double* __restrict__ HC, int cm, double z, double tw) {
+  const float zf = (float)z, opz = 1.f + zf, lz = lg2f_(opz);
+  const double dCt = dCt_from_dCr(P, HC, HC[HC_DH] * (double)iinv_at_z_f32(fc, zf));
+  const float Ez = E_at_z_f32(cr, zf, opz, lz);
+  const float dHE = cr.dH * rcpf_(Ez);
+  float ddL = (float)dCt + dHE * opz;
+  if (cm == CHB_COSMO_MG_FLRW) {
+    const float Xi = cr.Xi0 + (1.f - cr.Xi0) * ex2f_(-cr.n * lz);
+    ddL = ddL * Xi + ((float)dCt * opz) * (cr.n * (cr.Xi0 - 1.f) * ex2f_(-(cr.n + 1.f) * lz));
+  }
+  const double dVv = 12.566370614359172 * (double)dHE * dCt * dCt;
+  const double ckv = (double)(merger_rate_f32(cr, zf, lz) * rcpf_(opz) * rcpf_(ddL * opz * opz)) * tw;
+  return make_float2((float)dVv, (float)ckv);
+}
+
+// One thread per (hyper-point, event, k): full-occupancy evaluation of the z-grid terms, so that the
+// persistent numerator CTAs only stream 8 B per grid point instead of running a latency-bound phase.
+__global__ void __launch_bounds__(256)
+zgrid_terms_kernel(const NumArgs a, int h0, int nh) {
+  __shared__ double P[CHB_NPAR];
+  __shared__ double HC[CHB_NHC];
+  const int h = h0 + blockIdx.y;
+  if (threadIdx.x < CHB_NPAR) P[threadIdx.x] = a.hyper[(size_t)h * CHB_NPAR + threadIdx.x];
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + CHB_NHC) HC[threadIdx.x - 64] = a.HC[(size_t)h * CHB_NHC + threadIdx.x - 64];
+  __syncthreads();
+  const TableLayout lay = a.mc.lay;
+  const double* tblk = a.tabs + (size_t)h * lay.total() + lay.off_f32();
+  F32Consts fc = make_f32_consts(a.mc, P, HC, tblk);
+  const CosmoRateF32 cr = make_cosmo_rate_f32(a.mc, P, HC);
+  const long long n = (long long)a.Nev * a.Nz;
+  float2* out = a.zterms_out + (size_t)blockIdx.y * n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % a.Nz);
+    const double z = a.zgrids[i];
+    const double zl = (k > 0) ? a.zgrids[i - 1] : z, zr = (k < a.Nz - 1) ? a.zgrids[i + 1] : z;
+    out[i] = zgrid_terms_f32(fc, cr, P, HC, a.mc.cosmo_model, z, 0.5 * (zr - zl));
+  }
+  (void)nh;
+}
+cudaError_t launch_zgrid_terms(const NumArgs& a, int h0, int nh, cudaStream_t s) {
+  const long long n = (long long)a.Nev * a.Nz;
+  int gx = (int)std::min<long long>((n + 255) / 256, 148LL * 8);
+  dim3 grid(gx, nh);
+  zgrid_terms_kernel<<<grid, 256, 0, s>>>(a, h0, nh);
+  return cudaGetLastError();
+}
+
 #define FPHASE(i) do { if (a.prof && tid == 0) { long long _t = clock64(); pacc[i] += (unsigned long long)(_t - tlast); tlast = _t; } } while (0)
 
 __global__ void __launch_bounds__(F_NT, 2)
@@ -182,25 +234,18 @@ numerator_f32_kernel(const NumArgs a) {
     const float z_top = (float)P[CHB_P_ZMAX];
     // (fc.cd4_last is filled after the table copy has landed)
 
-    // ---- z-grid terms: warp 0 only, while the other warps already reweight samples (they need no
-    // staged table; results are consumed after the KDE) ----------------------------------------
-    if (warp == 0)
-    for (int k = lane; k < Nz; k += 32) {
-      const double z = zgrid[k];
-      const float zf = (float)z, opz = 1.f + zf, lz = lg2f_(opz);
-      const double dCt = dCt_from_dCr(P, HC, HC[HC_DH] * (double)iinv_at_z_f32(fc, zf));
-      const float Ez = E_at_z_f32(cr, zf, opz, lz);
-      const float dHE = cr.dH * rcpf_(Ez);
-      float Xi = 1.f;
-      float ddL = (float)dCt + dHE * opz;                                   // cosmo.py:212-221
-      if (cm == CHB_COSMO_MG_FLRW) {                                         // cosmo.py:245-257
-        Xi = cr.Xi0 + (1.f - cr.Xi0) * ex2f_(-cr.n * lz);
-        ddL = ddL * Xi + ((float)dCt * opz) * (cr.n * (cr.Xi0 - 1.f) * ex2f_(-(cr.n + 1.f) * lz));
+    // ---- z-grid terms: precomputed for all (hyper-point, event, k) by zgrid_terms_kernel when the
+    // buffer fits (a.zterms), otherwise evaluated here --------------------------------------------
+    if (a.zterms) {
+      const float2* zt = a.zterms + ((size_t)(h - a.zterms_h0) * a.Nev + ev) * Nz;
+      for (int k = tid; k < Nz; k += F_NT) { const float2 v = __ldg(zt + k); dV[k] = (double)v.x; ck[k] = (double)v.y; }
+    } else {
+      for (int k = tid; k < Nz; k += F_NT) {
+        const double z = zgrid[k];
+        const double zl = (k > 0) ? zgrid[k - 1] : z, zr = (k < Nz - 1) ? zgrid[k + 1] : z;
+        const float2 v = zgrid_terms_f32(fc, cr, P, HC, cm, z, 0.5 * (zr - zl));
+        dV[k] = (double)v.x; ck[k] = (double)v.y;
       }
-      const double zl = (k > 0) ? zgrid[k - 1] : z, zr = (k < Nz - 1) ? zgrid[k + 1] : z;
-      dV[k] = 12.566370614359172 * (double)dHE * dCt * dCt;                  // dVc/dz
-      // psi/(1+z) * trapezoid weight / (ddL/dz (1+z)^2)
-      ck[k] = (double)(merger_rate_f32(cr, zf, lz) * rcpf_(opz) * rcpf_(ddL * opz * opz)) * (0.5 * (zr - zl));
     }
     FPHASE(1);
     mbar_wait(&bar, phase);
