@@ -51,6 +51,7 @@ struct chb_handle {
   // events
   int64_t Nev = 0, Ns = 0, Nz = 0, P = 0, Ninj = 0;
   bool have_events = false, have_pixels = false, have_catalog = false, have_inj = false, dirty = true;
+  bool sorted = false;      // fp32 1-D kinds: samples of every event sorted by dL (windowed KDE, kde_f32.cuh)
   std::vector<double> h_m1, h_m2, h_dL, h_prior, h_ra, h_dec;      // host copies until prepare()
   std::vector<int64_t> h_pixels, h_pe_pix;
   std::vector<double> h_ra_pix;
@@ -305,9 +306,23 @@ static int prepare(chb_handle* h) {
     CU(cudaMemcpy(pr.data(), h->prior.p, n * sizeof(double), cudaMemcpyDeviceToHost), "D2H pe_prior");
     std::vector<float4> s4(n);
     std::vector<float2> l2(n);
-    for (size_t i = 0; i < n; ++i) {
-      s4[i] = make_float4((float)dl[i], (float)m1[i], (float)m2[i], (float)(1.0 / pr[i]));
-      l2[i] = make_float2((float)std::log2(m1[i]), (float)std::log2(m2[i]));
+    // 1-D KDE kinds: every per-event reduction is order-independent, so the packed copy is sorted by dL
+    // within each event.  z_from_dGW is monotone in dL, hence the reweighted z's come out sorted for every
+    // hyper-point and the windowed KDE only visits the grid points near each chunk of samples.
+    h->sorted = (h->cfg.kind_p_gw == CHB_PGW_1D || h->cfg.kind_p_gw == CHB_PGW_APPROX);
+    std::vector<int> perm(h->sorted ? Ns : 0);
+    for (int64_t e = 0; e < Nev; ++e) {
+      const size_t o = (size_t)e * Ns;
+      if (h->sorted) {
+        for (int64_t j = 0; j < Ns; ++j) perm[j] = (int)j;
+        const double* key = dl.data() + o;
+        std::sort(perm.begin(), perm.end(), [key](int x, int y) { return key[x] < key[y] || (key[x] == key[y] && x < y); });
+      }
+      for (int64_t j = 0; j < Ns; ++j) {
+        const size_t i = o + (h->sorted ? perm[j] : j);
+        s4[o + j] = make_float4((float)dl[i], (float)m1[i], (float)m2[i], (float)(1.0 / pr[i]));
+        l2[o + j] = make_float2((float)std::log2(m1[i]), (float)std::log2(m2[i]));
+      }
     }
     CU(h->s4.upload(s4.data(), n), "upload packed samples");
     CU(h->l2.upload(l2.data(), n), "upload log2 masses");
@@ -348,6 +363,7 @@ static int eval_impl(chb_handle* h, int64_t n_hyper, const double* d_hyper, doub
     a.binning = (c.kind_p_gw == CHB_PGW_FULL) ? 0 : c.binning; a.num_bins = c.num_bins; a.fp_mode = c.fp_mode;
     a.bw_value = c.bw_value; a.cut_grid = c.cut_grid; a.pe_neff = c.pe_neff;
     { const char* e = getenv("CHB_KDE_DIRECT"); a.rec_off = (e && e[0] == '1') ? 1 : 0; }
+    { const char* e = getenv("CHB_KDE_WIN"); a.kde_win_iters = e ? atoi(e) : 32; if (!h->sorted) a.kde_win_iters = 0; }
     a.Nev = (int)h->Nev; a.Ns = (int)h->Ns; a.Nz = (int)h->Nz; a.P = (int)std::max<int64_t>(h->P, 1);
     a.m1d = h->m1d.p; a.m2d = h->m2d.p; a.dL = h->dL.p; a.prior = h->prior.p; a.ra = h->ra.p; a.dec = h->dec.p;
     a.zgrids = h->zgrids.p; a.pix_off = h->pix_off.p; a.ra_pix = h->ra_pix.p; a.dec_pix = h->dec_pix.p;
@@ -379,8 +395,8 @@ static int eval_impl(chb_handle* h, int64_t n_hyper, const double* d_hyper, doub
       // fast path: 256-thread CTAs, float2 staging; two CTAs per SM when the plan fits in ~113 KB
       size_t fs = numerator_f32_smem_bytes(a);
       if (fs <= (size_t)h->max_smem_optin) {
-        CU(numerator_f32_configure(fs), "numerator_f32 smem opt-in");
-        int per_sm = numerator_f32_ctas_per_sm(fs);
+        CU(numerator_f32_configure(a.kind, fs), "numerator_f32 smem opt-in");
+        int per_sm = numerator_f32_ctas_per_sm(a.kind, fs);
         if (per_sm >= 1) {
           int grid = (int)std::min<long long>(units, (long long)h->sm_count * per_sm);
           h->num_grid = grid; h->num_smem = fs;

@@ -15,6 +15,7 @@ struct NumArgs {
   // hyperlikelihood options (likelihood.py:48-62)
   int kind, kernel, bw_method, use_cut, binning, num_bins, fp_mode;
   int rec_off;           // 1: disable the Gaussian recurrence (one MUFU.EX2 per pair), env CHB_KDE_DIRECT=1
+  int kde_win_iters;     // > 0: windowed recurrence over sorted samples, sub-stream iterations per chunk (env CHB_KDE_WIN, default 32; 0 = off)
   double bw_value, cut_grid, pe_neff;
   // event data, samples permuted so that each pixel's samples are contiguous
   int Nev, Ns, Nz, P;
@@ -73,8 +74,8 @@ long long numerator_scratch_doubles(const NumArgs& a);
 int numerator_block_threads();
 cudaError_t numerator_configure(size_t smem);
 size_t numerator_f32_smem_bytes(const NumArgs& a);
-cudaError_t numerator_f32_configure(size_t smem);
-int numerator_f32_ctas_per_sm(size_t smem);
+cudaError_t numerator_f32_configure(int kind, size_t smem);
+int numerator_f32_ctas_per_sm(int kind, size_t smem);
 cudaError_t launch_numerator_f32(const NumArgs& a, int grid, size_t smem, cudaStream_t s);
 cudaError_t launch_zgrid_terms(const NumArgs& a, int h0, int nh, cudaStream_t s);
 cudaError_t launch_catalog_collapse(int Nev, int P, int Nz, const double* p_cat, const double* gw_pdf, const int* neff_pix,

@@ -1,0 +1,275 @@
+// kde_win.cuh -- windowed Gaussian KDE pair sums for (nearly) SORTED samples on a uniform grid.
+//
+// Same sum as kde1d (utils/math.py:52-81) on the effective grid of likelihood.py:115-123:
+//     dens[g] = scale * sum_j w'_j 2^-(g' - x'_j)^2,   x' = (x - c) sqrt(log2(e)/2)/bw,  w' = w/W
+// organised so that every chunk of consecutive samples only visits the grid points where it can matter.
+//
+//  * The samples of an event are sorted by dL once at upload (api.cu prepare()); z_from_dGW is monotone
+//    in dL (cosmo.py:260-264), so the reweighted z's arrive sorted for every hyper-point and a chunk of
+//    64..256 consecutive samples spans only a few grid spacings.
+//  * Phase A (one pass over the samples): rescale {z, w} -> {x', log2 w'} in place and record per chunk
+//    {min x', max x', max log2 w', x' of that heaviest sample}.
+//  * Phase B (chunks x grid points, ~6000 cheap tests): a LOWER bound of the largest term at grid point g,
+//    M(g) = max_c [lw*_c - (g - x*_c)^2] from the chunks' heaviest samples, and for every chunk the hull of
+//    the grid points where its UPPER bound lwmax_c + log2(chunk) - dist(g, chunk)^2 reaches M(g) - T2.
+//    Everything outside that hull is below 2^-T2 = 1e-9 of the largest single term AT THAT GRID POINT, so the
+//    density keeps its relative accuracy in the far tails and in gaps -- the parts of the KDE that decide
+//    log-likelihoods of events sitting at a catalogue edge.  Correctness never depends on the sample order;
+//    only the size of the windows does.
+//  * Phase C: every warp takes chunks round-robin; a chunk's window is covered by passes of LPS lanes x R
+//    consecutive grid points per sample, 32/LPS samples in flight per warp.  Along a lane's run the Gaussian
+//    is advanced by the recurrence  2^-((d + r h)^2) = 2^-(d^2) q^r c^(r(r-1)/2),  q = 2^-(2 h d + h^2),
+//    with the sample-independent c^(r(r-1)/2) applied once per pass: 2 MUFU.EX2 per R pairs, and with the
+//    powers q, q^2, q^3, q^4 the accumulation costs R + R/4 + 2 FP32 instructions per R pairs.
+//    Runs that lie left of their chunk are walked right-to-left so that every run STARTS at its point nearest
+//    to the samples; when the nearest possible term is below 2^-64 the lane adds an integer exponent offset K
+//    so that the start value cannot flush to zero.  Partial sums go to a per-warp row of doubles (exact
+//    rescaling by 2^-K, no atomics, bit-reproducible).
+#pragma once
+#include "kde_f32.cuh"
+
+#define CHB_WIN_T2 30.0f          // terms below 2^-30 of the largest term at a grid point are dropped
+#define CHB_WIN_MAXR 16
+
+__device__ __forceinline__ float warp_min_f32(float v) {
+  float r; asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v)); return r;
+}
+__device__ __forceinline__ float warp_max_f32(float v) {
+  float r; asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v)); return r;
+}
+
+struct WinPlan { int R, LPS, chunk, nchunks; };
+
+// Tiling: among R in {4,8,12,16} (run-length bound (R-1) h <= 5.5) and LPS in {2,4,8} the pair with the fewest
+// instructions per sample for the typical window of 2 sqrt(T2 + 8)/h + 1 points (+ the spread of a chunk).
+// Returns false when windows cannot pay (window ~ whole grid, too few samples, grid too coarse).
+__device__ __forceinline__ bool win_plan(int G, int n, float h, int iters, int max_chunks, WinPlan& pl) {
+  if (!(h > 0.f) || h > 1.8f || iters <= 0) return false;
+  const int wn = 2 * (int)ceilf(6.2f / h) + 5;
+  if (10 * wn > 7 * G) return false;
+  float best = 1e30f;
+  pl.R = 0; pl.LPS = 0;
+  for (int l = 2, lg = 4; l <= 8; l <<= 1, --lg) {                     // lg = log2(32 / l)
+    for (int r = 4; r <= CHB_WIN_MAXR; r += 4) {
+      if ((float)(r - 1) * h > 5.5f) continue;
+      const int passes = (wn + l * r - 1) / (l * r);
+      const float per_lane = (float)(10 + r + r / 4) + (float)(2 * r * lg + 6 * r + 40) / (float)iters;
+      const float cost = (float)passes * per_lane * (float)l;
+      if (cost < best) { best = cost; pl.R = r; pl.LPS = l; }
+    }
+  }
+  if (pl.R == 0) return false;
+  pl.chunk = iters * (32 / pl.LPS);
+  while ((n + pl.chunk - 1) / pl.chunk > max_chunks) pl.chunk *= 2;
+  pl.nchunks = (n + pl.chunk - 1) / pl.chunk;
+  return pl.nchunks >= 8;
+}
+
+// Combine the 32/LPS sample sub-streams of a warp (lane bits >= LPS).  While the number of live values per lane
+// is even the exchange is a reduce-scatter (each lane keeps one half and receives the partner's copy of it),
+// so both the shuffle count and the values left to flush shrink geometrically; odd counts fall back to a
+// butterfly and only the lane with the bit clear stays `owner`.  On return the lane holds rs_final<V,O>()
+// sums for run offsets rbase .. rbase + that - 1.
+template <int V, int O> struct RsFinal { static constexpr int value = (V % 2 == 0) ? RsFinal<V / 2, O * 2>::value : RsFinal<V, O * 2>::value; };
+template <int V> struct RsFinal<V, 32> { static constexpr int value = V; };
+template <int V> struct RsFinal<V, 64> { static constexpr int value = V; };
+template <int V, int O, int N>
+__device__ __forceinline__ void rs_reduce(float (&a)[N], int lane, int& rbase, bool& owner) {
+  if constexpr (O < 32) {
+    if constexpr (V % 2 == 0) {
+      const bool up = (lane & O) != 0;
+#pragma unroll
+      for (int i = 0; i < V / 2; ++i) {
+        const float keep = up ? a[i + V / 2] : a[i];
+        const float send = up ? a[i] : a[i + V / 2];
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, O);
+      }
+      rbase += up ? V / 2 : 0;
+      rs_reduce<V / 2, O * 2, N>(a, lane, rbase, owner);
+    } else {
+#pragma unroll
+      for (int i = 0; i < V; ++i) a[i] += __shfl_xor_sync(0xffffffffu, a[i], O);
+      owner = owner && ((lane & O) == 0);
+      rs_reduce<V, O * 2, N>(a, lane, rbase, owner);
+    }
+  }
+}
+
+template <int R, int LPS>
+__device__ __forceinline__ void kde_win_pass(const float2* __restrict__ xl, int cb, int ce, int gb, int glast,
+                                             float4 sm4, double gfirst, double hd, float h,
+                                             const float* __restrict__ cr, double* __restrict__ row) {
+  static_assert(R % 4 == 0 && R <= CHB_WIN_MAXR, "run length");
+  constexpr int S = 32 / LPS;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % LPS, sub = lane / LPS;
+  const int g0 = gb + gl * R;
+  const float run_lo = (float)(gfirst + (double)g0 * hd), run_hi = run_lo + (float)(R - 1) * h;
+  const bool rev = run_hi < sm4.x;                       // run entirely left of the chunk: walk it right-to-left
+  const int gs = rev ? g0 + R - 1 : g0;
+  const float hs = rev ? -h : h;
+  const float gp = (float)(gfirst + (double)gs * hd);
+  const float dr = rev ? sm4.x - run_hi : fmaxf(run_lo - sm4.y, 0.f);
+  const float top = sm4.z - dr * dr;                     // largest exponent any term of this run can have
+  const float Kf = (top > -64.f) ? 0.f : fminf(floorf(100.f - top), 1900.f);
+  const float m2h = -2.f * hs, mh2 = -h * h;
+  float acc[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) acc[r] = 0.f;
+#pragma unroll 4
+  for (int j = cb + sub; j < ce; j += S) {
+    const float2 v = xl[j];
+    const float d = gp - v.x;
+    const float e0 = ex2_ftz(fmaf(-d, d, v.y) + Kf);                   // w' 2^(K - d^2)
+    const float q = ex2_ftz(fminf(fmaf(d, m2h, mh2), 31.f));
+    const float q2 = q * q, q3 = q2 * q, q4 = q2 * q2;
+    float p = e0;
+#pragma unroll
+    for (int b = 0; b < R; b += 4) {
+      if (b) p *= q4;
+      acc[b] += p;
+      acc[b + 1] = fmaf(p, q, acc[b + 1]);
+      acc[b + 2] = fmaf(p, q2, acc[b + 2]);
+      acc[b + 3] = fmaf(p, q3, acc[b + 3]);
+    }
+  }
+  int rbase = 0;
+  bool owner = true;
+  rs_reduce<R, LPS, R>(acc, lane, rbase, owner);
+  constexpr int VF = RsFinal<R, LPS>::value;
+  // exact 2^-K as a double (|K| <= 1900 needs two factors)
+  const int K = (int)Kf, K1 = K / 2, K2 = K - K1;
+  const double sc = __hiloint2double((1023 - K1) << 20, 0) * __hiloint2double((1023 - K2) << 20, 0);
+  const int step = rev ? -1 : 1;
+#pragma unroll
+  for (int i = 0; i < VF; ++i) {
+    const int r = rbase + i;
+    const int g = gs + step * r;
+    if (owner && g <= glast) row[g] += (double)(acc[i] * cr[r]) * sc;
+  }
+}
+
+// Phase C driver: the passes of all chunks form one list (pend[c] = inclusive prefix sum of passes per chunk,
+// kept in the .w slot of the chunk table); warp w takes the contiguous slice [w T/NW, (w+1) T/NW) of it, so the
+// extra passes of the wide edge chunks are spread over the warps and the split is the same on every run.
+template <int R, int LPS, int NW>
+__device__ __forceinline__ void kde_win_chunks(const float2* __restrict__ xl, int n, int G, double gfirst, double hd,
+                                               const WinPlan& pl, const float4* __restrict__ summ,
+                                               const int2* __restrict__ win, int total, const float* __restrict__ cr,
+                                               double* __restrict__ rows) {
+  constexpr int W = LPS * R;
+  const int warp = threadIdx.x >> 5;
+  const float h = (float)hd;
+  double* row = rows + warp * G;
+  const int i0 = (int)(((long long)warp * total) / NW), i1 = (int)(((long long)(warp + 1) * total) / NW);
+  int c = 0;
+  for (int it = i0; it < i1; ++it) {
+    while (it >= __float_as_int(summ[c].w)) ++c;
+    const int2 w = win[c];
+    const int np = (w.y - w.x + W) / W;
+    const int gb = w.x + (it - (__float_as_int(summ[c].w) - np)) * W;
+    const int cb = c * pl.chunk, ce = min(n, cb + pl.chunk);
+    kde_win_pass<R, LPS>(xl, cb, ce, gb, w.y, summ[c], gfirst, hd, h, cr, row);
+    __syncwarp();
+  }
+}
+
+// Whole-CTA call (NW warps).  xw: in {x, w} (x sorted or not), out {x', log2 w'}.  Scratch: summ/win hold
+// pl.nchunks entries, cr 16 floats + 1 int, rows NW*G doubles.  dens[g] = scale * sum_j w'_j 2^-(g'_g - x'_j)^2 with
+// g'_g = (lb + g step - c) sf, sf = float(s) shared by samples and grid.
+template <int NW>
+__device__ __forceinline__ void kde1d_f32_win(float2* __restrict__ xw, int n, int G, double lb, double step, double c,
+                                              double s, double W, const WinPlan& pl, double scale,
+                                              float4* __restrict__ summ, int2* __restrict__ win, float* __restrict__ cr,
+                                              double* __restrict__ rows, double* __restrict__ dens) {
+  int* total_passes = reinterpret_cast<int*>(cr + 16);                 // cr: 16 floats + 1 int of scratch
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float sf = (float)s;
+  const double gfirst = (lb - c) * (double)sf, hd = step * (double)sf;
+  const float h = (float)hd;
+  const float c_hi = (float)c, c_lo = (float)(c - (double)c_hi);
+  const float lg2invW = -lg2f_((float)W);
+  // ---- phase A: rescale + chunk summaries ----------------------------------------------------
+  for (int i = threadIdx.x; i < NW * G; i += NW * 32) rows[i] = 0.0;
+  if (threadIdx.x < 16) cr[threadIdx.x] = exp2f(-(h * h) * (float)(threadIdx.x * (threadIdx.x - 1)));
+  for (int ck = warp; ck < pl.nchunks; ck += NW) {
+    const int cb = ck * pl.chunk, ce = min(n, cb + pl.chunk);
+    float lo = INFINITY, hi = -INFINITY, lm = -INFINITY, xm = 0.f;
+    for (int j = cb + lane; j < ce; j += 32) {
+      const float2 v = xw[j];
+      const float x = ((v.x - c_hi) - c_lo) * sf;
+      const bool live = v.y > 0.f;                                     // zero / NaN weights add exactly 0
+      const float lw = live ? lg2f_(v.y) + lg2invW : -INFINITY;
+      xw[j] = make_float2(x, lw);
+      lo = fminf(lo, live ? x : INFINITY);
+      hi = fmaxf(hi, live ? x : -INFINITY);
+      if (lw > lm) { lm = lw; xm = x; }
+    }
+    lo = warp_min_f32(lo); hi = warp_max_f32(hi);
+    const float lmw = warp_max_f32(lm);
+    const unsigned pick = __ballot_sync(0xffffffffu, lm == lmw && lm > -INFINITY);
+    const float xmw = __shfl_sync(0xffffffffu, xm, pick ? (__ffs(pick) - 1) : 0);
+    if (lane == 0) {
+      summ[ck] = make_float4(lo, hi, pick ? lmw : -INFINITY, xmw);
+      win[ck] = make_int2(G, -1);
+    }
+  }
+  __syncthreads();
+  // ---- phase B: per grid point the lower bound M(g); per chunk the hull of the points it can matter at ----
+  const float lgchunk = lg2f_((float)pl.chunk);
+  for (int gbase = warp * 32; gbase < G; gbase += NW * 32) {
+    const int g = gbase + lane;
+    const float gp = (float)(gfirst + (double)g * hd);
+    float m = -INFINITY;
+    for (int ck = 0; ck < pl.nchunks; ++ck) {
+      const float4 s4 = summ[ck];
+      const float d = gp - s4.w;
+      m = fmaxf(m, fmaf(-d, d, s4.z));
+    }
+    const float thr = m - CHB_WIN_T2;
+    for (int ck = 0; ck < pl.nchunks; ++ck) {
+      const float4 s4 = summ[ck];
+      const float dist = fmaxf(fmaxf(s4.x - gp, gp - s4.y), 0.f);
+      const bool need = (g < G) && (s4.z > -INFINITY) && (fmaf(-dist, dist, s4.z + lgchunk) >= thr);
+      const unsigned b = __ballot_sync(0xffffffffu, need);
+      if (b && lane == 0) {
+        atomicMin(&win[ck].x, gbase + __ffs(b) - 1);
+        atomicMax(&win[ck].y, gbase + 31 - __clz(b));
+      }
+    }
+  }
+  __syncthreads();
+  // ---- phase C: pair sums ------------------------------------------------------------------------
+  if (warp == 0) {                                                     // passes per chunk -> inclusive prefix sums
+    const int W = pl.LPS * pl.R;
+    int carry = 0;
+    for (int base = 0; base < pl.nchunks; base += 32) {
+      const int ck = base + lane;
+      int x = 0;
+      if (ck < pl.nchunks) { const int2 w = win[ck]; x = (w.x <= w.y) ? (w.y - w.x + W) / W : 0; }
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+      if (ck < pl.nchunks) summ[ck].w = __int_as_float(carry + x);
+      carry += __shfl_sync(0xffffffffu, x, 31);
+    }
+    if (lane == 0) *total_passes = carry;
+  }
+  __syncthreads();
+  const int total = *total_passes;
+#define CHB_WIN_CASE(RR, LL) case RR * 16 + LL: kde_win_chunks<RR, LL, NW>(xw, n, G, gfirst, hd, pl, summ, win, total, cr, rows); break;
+  switch (pl.R * 16 + pl.LPS) {
+    CHB_WIN_CASE(4, 2) CHB_WIN_CASE(4, 4) CHB_WIN_CASE(4, 8)
+    CHB_WIN_CASE(8, 2) CHB_WIN_CASE(8, 4) CHB_WIN_CASE(8, 8)
+    CHB_WIN_CASE(12, 2) CHB_WIN_CASE(12, 4) CHB_WIN_CASE(12, 8)
+    CHB_WIN_CASE(16, 2) CHB_WIN_CASE(16, 4) CHB_WIN_CASE(16, 8)
+    default: break;
+  }
+#undef CHB_WIN_CASE
+  __syncthreads();
+  for (int g = threadIdx.x; g < G; g += NW * 32) {
+    double acc = 0.0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) acc += rows[w * G + g];
+    dens[g] = acc * scale;
+  }
+}

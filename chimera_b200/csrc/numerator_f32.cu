@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "models_f32.cuh"
 #include "kde_f32.cuh"
+#include "kde_win.cuh"
 #include "stage.cuh"
 #include <algorithm>
 
@@ -33,8 +34,8 @@ __host__ __device__ inline FPlan make_fplan(int tab_doubles, int Nz, int B, int 
   p.zgrid = o; o += Nz;
   p.dV = o; o += Nz;
   p.ck = o; o += Nz;
-  p.pgw = o; o += Nz;
   p.eg = o; o += Nz;
+  p.pgw = o; o += Nz;          // pgw | dens are contiguous: the windowed KDE keeps its chunk tables there
   p.dens = o; o += Nz;
   p.bc = o; o += B;
   p.bs = o; o += B;
@@ -170,6 +171,9 @@ cudaError_t launch_zgrid_terms(const NumArgs& a, int h0, int nh, cudaStream_t s)
 
 #define FPHASE(i) do { if (a.prof && tid == 0) { long long _t = clock64(); pacc[i] += (unsigned long long)(_t - tlast); tlast = _t; } } while (0)
 
+// KG: kind group the kernel is compiled for (0: '1d'/'approximate', 1: 'marginalized', 2: 'full') -- one
+// instantiation per group keeps the instruction footprint of the hot 1-D path small.
+template <int KG>
 __global__ void __launch_bounds__(F_NT, 2)
 numerator_f32_kernel(const NumArgs a) {
   extern __shared__ __align__(16) double sm[];
@@ -178,6 +182,7 @@ numerator_f32_kernel(const NumArgs a) {
   __shared__ double HC[CHB_NHC];
   __shared__ double L[8];
   __shared__ int next_chunk;
+  __shared__ float crs[20];
 
   const TableLayout lay = a.mc.lay;
   const int Ns = a.Ns, Nz = a.Nz, Pp = a.P, B = a.binning ? a.num_bins : 0;
@@ -256,6 +261,10 @@ numerator_f32_kernel(const NumArgs a) {
     // ---- stage 1: reweighting (pop_wrapper.py:67-80) ------------------------------------------
     const size_t so = (size_t)ev * Ns;
     Stats6 st = {0.0, 0.0, 0.0, 0.0, INFINITY, -INFINITY};
+    // per-thread partial statistics in fp32 (a thread sees ~Ns/256 samples), z shifted by the redshift of the
+    // event's median-dL sample so that the one-pass variance does not cancel; fp64 from the block reduction on
+    float fa = 0.f, fb = 0.f, fcs = 0.f, fd = 0.f;
+    const float z0 = z_from_dL_f32(fc, __ldg(&a.s4[(size_t)ev * Ns + Ns / 2].x));
     {
       // four samples in flight per thread, identical instruction stream for all of them (branch-free
       // weights, fixed two-step table scan) so the compiler interleaves their dependency chains
@@ -298,19 +307,21 @@ numerator_f32_kernel(const NumArgs a) {
           const int j = jb + u * 32;
           if (j < Ns) {
             zw[j] = make_float2(zf[u], wf[u]);
-            const double z = (double)zf[u], w = (double)wf[u];
-            st.a += w; st.b += w * w; st.c += z; st.d += z * z;
+            const float dz = zf[u] - z0;
+            fa += wf[u]; fb = fmaf(wf[u], wf[u], fb); fcs += dz; fd = fmaf(dz, dz, fd);
             st.mn = fminf(st.mn, zf[u]); st.mx = fmaxf(st.mx, zf[u]);
           }
         }
       }
     }
     FPHASE(2);
+    st.a = (double)fa; st.b = (double)fb; st.c = (double)fcs; st.d = (double)fd;
     st = block_stats(st, red);
     const double s1 = st.a, s2 = st.b;
     const double zmn = (double)st.mn, zmx = (double)st.mx;
-    const double zmean = st.c / Ns;
-    const double zstd = sqrt(fmax(st.d / Ns - zmean * zmean, 0.0));      // one-pass variance in fp64
+    const double dzmean = st.c / Ns;
+    const double zstd = sqrt(fmax(st.d / Ns - dzmean * dzmean, 0.0));    // one-pass variance about z0
+    const double zmean = (double)z0 + dzmean;
     const double norm = s1 / Ns;                  // likelihood.py:111
     const double neff = s1 * s1 / s2;             // likelihood.py:112
     const bool ok = (a.kind == CHB_PGW_FULL) ? !(neff < a.pe_neff) : (neff >= a.pe_neff);
@@ -348,7 +359,7 @@ numerator_f32_kernel(const NumArgs a) {
     const double* pcat_ev = has_cat ? a.p_cat + (size_t)ev * Pp * Nz : nullptr;
     const double* pcompl_ev = has_cat ? a.P_compl + (size_t)ev * Nz : nullptr;
 
-    if (a.kind == CHB_PGW_1D || a.kind == CHB_PGW_APPROX) {
+    if (KG == 0) {
       float2* dxw = zw;
       int dn = Ns;
       double W = s1, Q = s2, dstd = zstd;
@@ -383,7 +394,21 @@ numerator_f32_kernel(const NumArgs a) {
       if (a.bw_method == CHB_BW_SCOTT) bw = pow(neff_k, -0.2) * dstd;
       else if (a.bw_method == CHB_BW_SILVERMAN) bw = pow(neff_k * 3.0 / 4.0, -0.2) * dstd;
       else bw = a.bw_value * dstd;
-      kde_inplace(dxw, dn, eg, G, bw, W, a.kernel, norm, part, F_NW * Nz, dens, ustep);
+      bool windowed = false;
+      if (a.kernel == CHB_KERNEL_GAUSS && ustep > 0.0 && a.kde_win_iters > 0 && !a.binning && G >= 2) {
+        // windowed recurrence over the sorted samples (kde_win.cuh); chunk tables live in pgw | dens
+        const double s = 0.8493218002880191 / bw;
+        WinPlan wp;
+        const int maxc = (2 * Nz * (int)sizeof(double)) / (int)(sizeof(float4) + sizeof(int2));
+        if (win_plan(G, dn, (float)(ustep * (double)(float)s), a.kde_win_iters, maxc, wp)) {
+          float4* summ = reinterpret_cast<float4*>(pgw);
+          int2* win = reinterpret_cast<int2*>(summ + maxc);
+          kde1d_f32_win<F_NW>(dxw, dn, G, eg[0], ustep, 0.5 * (eg[0] + eg[G - 1]), s, W, wp,
+                              norm * 0.3989422804014327 / bw, summ, win, crs, reinterpret_cast<double*>(part), dens);
+          windowed = true;
+        }
+      }
+      if (!windowed) kde_inplace(dxw, dn, eg, G, bw, W, a.kernel, norm, part, F_NW * Nz, dens, ustep);
       __syncthreads();
       for (int k = tid; k < Nz; k += F_NT) pgw[k] = interp_lr(zgrid[k], eg, dens, G, 0.0, 0.0);
       __syncthreads();
@@ -412,7 +437,7 @@ numerator_f32_kernel(const NumArgs a) {
           }
         }
       }
-    } else if (a.kind == CHB_PGW_MARG) {
+    } else if (KG == 1) {
       // ---- p_gw3dmarg: per pixel, always Epanechnikov (likelihood.py:160-205) -----------------
       const int* off = a.pix_off + (size_t)ev * (Pp + 2);
       const double* gwp = a.gw_pdf + (size_t)ev * Pp;
@@ -595,15 +620,30 @@ numerator_f32_kernel(const NumArgs a) {
   if (a.prof && tid == 0) for (int i = 0; i < 8; ++i) a.prof[(size_t)blockIdx.x * 8 + i] = pacc[i];
 }
 
-cudaError_t numerator_f32_configure(size_t smem) {
-  return cudaFuncSetAttribute(numerator_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+static inline int kind_group(int kind) { return kind == CHB_PGW_MARG ? 1 : (kind == CHB_PGW_FULL ? 2 : 0); }
+cudaError_t numerator_f32_configure(int kind, size_t smem) {
+  switch (kind_group(kind)) {
+    case 0: return cudaFuncSetAttribute(numerator_f32_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    case 1: return cudaFuncSetAttribute(numerator_f32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    default: return cudaFuncSetAttribute(numerator_f32_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  }
 }
-int numerator_f32_ctas_per_sm(size_t smem) {
+int numerator_f32_ctas_per_sm(int kind, size_t smem) {
   int n = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, numerator_f32_kernel, F_NT, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+  cudaError_t e;
+  switch (kind_group(kind)) {
+    case 0: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, numerator_f32_kernel<0>, F_NT, smem); break;
+    case 1: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, numerator_f32_kernel<1>, F_NT, smem); break;
+    default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, numerator_f32_kernel<2>, F_NT, smem); break;
+  }
+  if (e != cudaSuccess) { cudaGetLastError(); return 0; }
   return n;
 }
 cudaError_t launch_numerator_f32(const NumArgs& a, int grid, size_t smem, cudaStream_t s) {
-  numerator_f32_kernel<<<grid, F_NT, smem, s>>>(a);
+  switch (kind_group(a.kind)) {
+    case 0: numerator_f32_kernel<0><<<grid, F_NT, smem, s>>>(a); break;
+    case 1: numerator_f32_kernel<1><<<grid, F_NT, smem, s>>>(a); break;
+    default: numerator_f32_kernel<2><<<grid, F_NT, smem, s>>>(a); break;
+  }
   return cudaGetLastError();
 }

@@ -258,3 +258,39 @@ def test_compute_z_grids(cb, golden_setup):
   close(cb.compute_z_grids(fid, th, None, 40, [1., 99.]), g["zgrid_pct"], 1e-11)
   mg = cb.cosmo.mg_flrw(H0=70., Om0=0.25, z_max=5.)
   close(cb.compute_z_grids(mg, th, {"H0": [50., 90.], "Xi0": [0.5, 2.], "n": [1., 3.]}, 40), g["zgrid_mg"], 1e-11)
+
+
+@pytest.mark.parametrize("kind,zmax", [(None, 0.45), (None, 5.0), ("approximate", 0.6)])
+def test_windowed_kde_bulk_and_tails(cb, kind, zmax):
+  """fp32 mode with enough samples for the windowed recurrence (kde_win.cuh).  A truncated rate model
+  (psi = 0 above zmax, rate.py:118-129) makes the likelihood of every event beyond zmax an integral over
+  the FAR LOWER TAIL of its KDE, so this checks that the windows keep the tails exact (fp64 oracle)."""
+  from oracle import chimera_oracle as orc
+  sky = kind is not None
+  ev, zg, inj, N_inj, cat = _synthetic(16, 4096, 300, 20000, sky, seed=300 + (5 if sky else 0))
+  kw = dict(m1det=ev["m1det"], m2det=ev["m2det"], dL=ev["dL"], pe_prior=ev["pe_prior"])
+  gcat = None
+  if sky:
+    kw.update({k: ev[k] for k in ("ra", "dec", "opt_nsides", "pixels_opt_nsides", "ra_pix", "dec_pix", "gw_loc2d_pdf",
+                                  "pixels_pe_opt_nside")})
+    gcat = cb.pixelated_catalog(cb.dVdz_completeness(cat["z_range"]), p_cat=cat["p_cat"], P_compl=cat["P_compl"])
+  th = cb.theta_pe_det(**kw)
+  sel = cb.selection_function(cb.theta_inj_det(**inj), N_inj, 5.)
+  pop = cb.population(cb.cosmo.flrw(z_max=5.), cb.mass.plp(), cb.rate.trunc_madau_dickinson(zmax=zmax), gal_cat=gcat)
+  like = cb.hyperlikelihood(th, zg, pop, sel, kind_p_gw3d=kind, kernel="gauss", binning=False, fp_mode="fp32")
+  pop0 = orc.make_pop(orc.make_cosmo("flrw", z_max=5.), orc.make_mass("plp"),
+                      orc.make_rate("trunc_madau_dickinson", zmax=zmax), catalog=cat)
+  opts = orc.make_opts(kind, "gauss", None, 2.0, False, 200, 2.0)
+  H0 = np.array([50., 70., 95.])
+  lle = like.compute_all(H0=H0)[0]
+  n_tail = 0
+  for h, h0 in enumerate(H0):
+    ref = orc.compute_all(pop0, ev, zg, opts, inj, N_inj, 5., ev.get("neff_pixels"), H0=float(h0))[0]
+    fin = np.isfinite(ref) & (np.abs(ref) < 1e300)
+    assert np.array_equal(fin, np.isfinite(lle[h]) & (np.abs(lle[h]) < 1e300))
+    # |d log L| relative to max(|log L|, 1): log-likelihoods cross zero, likelihoods carry the relative error
+    err = np.abs(lle[h][fin] - ref[fin]) / np.maximum(np.abs(ref[fin]), 1.0)
+    assert err.max() < 2e-4, (h0, err.max(), lle[h][fin][np.argmax(err)], ref[fin][np.argmax(err)])
+    n_tail += int(np.sum(ref[fin] < -30.))
+  if zmax < 1.0:
+    assert n_tail > 0      # the case really contains tail-dominated events
