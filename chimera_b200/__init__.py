@@ -13,3 +13,5 @@ from .catalog import completeness, empty_catalog, pixelated_catalog, dVdz_comple
 from .likelihood import hyperlikelihood
 from .selection_function import selection_function
 from . import parallel
+from . import sky
+from .sky import pixelize_gw_catalog

@@ -67,6 +67,11 @@ EXPORTS = {
   "chb_last_timings": (C.c_int, [_hp, _dp]),
   "chb_phase_profile": (C.c_int, [_hp, C.c_int, _dp]),
   "chb_mufu_peak": (C.c_int, [C.c_int, C.c_double, _dp]),
+  "chb_healpix_ang2pix_ring": (C.c_int, [C.c_int, C.c_int64, C.c_int64, _dp, _dp, _ip]),
+  "chb_healpix_pix2ang_ring": (C.c_int, [C.c_int, C.c_int64, C.c_int64, _ip, _dp, _dp]),
+  "chb_pixelize_samples": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int64, _ip, _dp, _dp, _ip, _dp, _dp, _ip, _dp]),
+  "chb_precompute_p_cat": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int64, _dp, _dp, _ip, _ip, C.POINTER(C.c_int32),
+                                     C.c_int64, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
 }
 
 _lib = None

@@ -6,8 +6,10 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libchimera_b200.so")
-SOURCES = ["tables.cu", "selection.cu", "numerator.cu", "numerator_f32.cu", "api.cu", "microbench.cu"]
-HEADERS = ["models.cuh", "models_f32.cuh", "kde_f32.cuh", "common.cuh", "stage.cuh", os.path.join("..", "..", "include", "chimera_b200.h")]
+SOURCES = ["tables.cu", "selection.cu", "numerator.cu", "numerator_f32.cu", "api.cu", "microbench.cu", "setup.cu"]
+# setup.cu holds the HEALPix index arithmetic: no FMA contraction, so that it rounds like the host libraries
+EXTRA_FLAGS = {"setup.cu": ["-fmad=false"]}
+HEADERS = ["models.cuh", "models_f32.cuh", "kde_f32.cuh", "kde_win.cuh", "common.cuh", "stage.cuh", os.path.join("..", "..", "include", "chimera_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 
@@ -31,7 +33,7 @@ def build(force=False, verbose=False):
   procs = []
   for s in SOURCES:
     o = os.path.join(HERE, "build", s.replace(".cu", ".o"))
-    cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, s), "-o", o]
+    cmd = [nvcc] + flags + EXTRA_FLAGS.get(s, []) + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, s), "-o", o]
     procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     objs.append(o)
   for s, p in procs:

@@ -4,9 +4,8 @@
 
 In the likelihood the assembly `fR * p_cat + (1 - P_compl) * p_bkg` is fused into the CUDA
 numerator kernel (csrc/numerator.cu); `p_gal` below is the inspection entry point.
-`precompute_p_cat` (setup, once per run) currently runs on the host."""
+`precompute_p_cat` (setup, once per run) runs on the GPU through `chb_precompute_p_cat`."""
 import numpy as np
-from .. import healpix
 from ..population.cosmo import dVcdz_at_z
 
 _trapz = np.trapezoid if hasattr(np, "trapezoid") else np.trapz
@@ -73,40 +72,26 @@ class pixelated_catalog(object):
 
   def precompute_p_cat(self, zgrids):
     """p_cat[e, i, :] = sum_g w_g N(z; z_g, s_g) dVc/dz(z) / norm_g / sum_g w_g over the galaxies in
-    pixel i of event e with z strictly inside the event grid (catalog.py:143-231); -100 padding."""
-    zgrids = np.asarray(zgrids, dtype=np.float64)
-    nsides = np.asarray(self.data_gw_pixelated.opt_nsides)
-    pixels = np.asarray(self.data_gw_pixelated.pixels_opt_nsides)
+    pixel i of event e with z strictly inside the event grid (catalog.py:143-231); -100 padding.
+    Runs on the GPU (`chb_precompute_p_cat`, csrc/setup.cu): HEALPix ids of the galaxies at every nside in
+    use, bucketing by pixel, then one CTA per (event, pixel)."""
+    import ctypes as C
+    from .. import _lib
+    zgrids = _lib.f64(zgrids)
+    nsides = _lib.i64(self.data_gw_pixelated.opt_nsides)
+    pixels = _lib.i64(self.data_gw_pixelated.pixels_opt_nsides)
     nev, P = pixels.shape
     nz = zgrids.shape[1]
     g = self.data_gal
-    order, spix = {}, {}
-    for ns in np.unique(nsides):
-      gp = healpix.find_pix_RAdec(g['ra'], g['dec'], int(ns))
-      order[int(ns)] = np.argsort(gp, kind="stable")
-      spix[int(ns)] = gp[order[int(ns)]]
-    p_cat = np.full((nev, P, nz), -100.)
-    N_gal = np.zeros(nev)
-    for e in range(nev):
-      ns = int(nsides[e])
-      zg = zgrids[e]
-      dv = np.asarray(dVcdz_at_z(self.cosmo, zg))
-      for i in range(int(self.neff_pixels[e])):
-        a, b = np.searchsorted(spix[ns], [pixels[e, i], pixels[e, i] + 1])
-        idx = order[ns][a:b]
-        zgal, sg, wg = g['z'][idx], g['z_err'][idx], g['w'][idx]
-        m = (zgal > zg[0]) & (zgal < zg[-1])
-        zgal, sg, wg = zgal[m], sg[m], wg[m]
-        N_gal[e] += zgal.size
-        if zgal.size == 0:
-          p_cat[e, i] = 0.
-          continue
-        with np.errstate(all="ignore"):
-          gauss = np.power(2 * np.pi * sg ** 2, -0.5) * np.exp(-0.5 * ((zg[:, None] - zgal) / sg) ** 2) * dv[:, None]
-          norm = _trapz(gauss, zg[:, None], axis=0)
-          row = np.sum(wg * gauss / norm, axis=1) / np.sum(wg)
-        row[~np.isfinite(row)] = 0.
-        p_cat[e, i] = row
+    dv = _lib.f64(np.asarray(dVcdz_at_z(self.cosmo, zgrids)).reshape(nev, nz))     # fiducial cosmology, on the GPU
+    gra, gdec, gz, ge, gw = (_lib.f64(g[k]) for k in ("ra", "dec", "z", "z_err", "w"))
+    neff = np.ascontiguousarray(self.neff_pixels, dtype=np.int32)
+    p_cat = np.empty((nev, P, nz), dtype=np.float64)
+    N_gal = np.zeros(nev, dtype=np.float64)
+    _lib.check(_lib.load().chb_precompute_p_cat(
+      int(getattr(self, "device", 0)), nev, P, nz, _lib.dptr(zgrids), _lib.dptr(dv), _lib.iptr(nsides), _lib.iptr(pixels),
+      neff.ctypes.data_as(C.POINTER(C.c_int32)), gz.size, _lib.dptr(gra), _lib.dptr(gdec), _lib.dptr(gz), _lib.dptr(ge),
+      _lib.dptr(gw), _lib.dptr(p_cat), _lib.dptr(N_gal)))
     self.p_cat = p_cat
     self.N_gal = N_gal
     self.P_compl = self.completeness.P_compl(zgrids)[:, np.newaxis, :]

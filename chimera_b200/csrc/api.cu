@@ -82,6 +82,7 @@ static int fail(chb_handle* h, int code, const std::string& msg) {
 static int cuda_fail(chb_handle* h, cudaError_t e, const char* what) {
   return fail(h, CHB_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
+int chb_fail_global(int code, const char* msg) { return fail(nullptr, code, msg ? msg : ""); }   // setup.cu
 #define CU(call, what) do { cudaError_t _e = (call); if (_e != cudaSuccess) return cuda_fail(h, _e, what); } while (0)
 
 static int validate_cfg(const chb_config* c, std::string& why) {

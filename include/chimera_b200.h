@@ -198,6 +198,36 @@ int chb_phase_profile(chb_handle* h, int enable, double out[8]);
  * denominator of the KDE roofline fraction. */
 int chb_mufu_peak(int device, double seconds, double* exp_per_s);
 
+/* ---- Setup-side callers of the path, stateless, host pointers ------------------
+ * HEALPix RING indexing, replacing healpy.ang2pix / healpy.pix2ang as called at CHIMERA/utils/angles.py:45,58,71
+ * (nest=False): theta = colatitude in [0, pi], phi = longitude [rad]; pix int64 in [0, 12 nside^2).
+ * nside must be a power of two (ValueError otherwise, like healpy). */
+int chb_healpix_ang2pix_ring(int device, int64_t nside, int64_t n, const double* theta, const double* phi,
+                             int64_t* pix);
+int chb_healpix_pix2ang_ring(int device, int64_t nside, int64_t n, const int64_t* pix, double* theta, double* phi);
+
+/* The per-sample part of pixelize_gw_catalog (CHIMERA/data.py:316-345) for events whose pixel sets are known:
+ * pixels_pe_opt_nside (Nev x Ns): the sample's own pixel at opt_nsides[ev] if it is one of the event's pixels,
+ *   else the event pixel with the smallest angular separation (utils/angles.py:146-160, numpy.argmin rule);
+ * gw_loc2d_pdf (Nev x P): 2-D Gaussian KDE of the (ra, dec) samples at the pixel centres
+ *   (jax_gkde_nd, utils/math.py:95-148), -100 in padded slots.
+ * Inputs: ra/dec (Nev x Ns) [rad]; pixels_opt_nsides, ra_pix, dec_pix (Nev x P) padded with -100.
+ * Either output may be NULL. */
+int chb_pixelize_samples(int device, int64_t Nev, int64_t Ns, int64_t P, const int64_t* opt_nsides,
+                         const double* ra, const double* dec, const int64_t* pixels_opt_nsides,
+                         const double* ra_pix, const double* dec_pix, int64_t* pixels_pe_opt_nside,
+                         double* gw_loc2d_pdf);
+
+/* pixelated_catalog.precompute_p_cat (CHIMERA/catalog/catalog.py:143-195, _sum_gaussians_ucv :209-221):
+ * p_cat (Nev x P x Nz) = per (event, pixel) sum over the pixel's galaxies with z strictly inside the event grid
+ * of w N(z_k; z_gal, z_err) dVdz[ev,k] / trapz_k(...) / sum w; non-finite -> 0; padded pixel slots -100.
+ * dVdz (Nev x Nz) is dVc/dz of the catalogue's fiducial cosmology on z_grids (chb_model_eval, CHB_F_DVCDZ_AT_Z).
+ * Galaxies (Ngal): ra, dec [rad], z, z_err (= z_err (1+z), catalog.py:113), w.  N_gal (Nev) may be NULL. */
+int chb_precompute_p_cat(int device, int64_t Nev, int64_t P, int64_t Nz, const double* z_grids, const double* dVdz,
+                         const int64_t* opt_nsides, const int64_t* pixels_opt_nsides, const int32_t* neff_pixels,
+                         int64_t Ngal, const double* gal_ra, const double* gal_dec, const double* gal_z,
+                         const double* gal_zerr, const double* gal_w, double* p_cat, double* N_gal);
+
 #ifdef __cplusplus
 }
 #endif
