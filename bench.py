@@ -203,6 +203,19 @@ def measured_peaks():
   return 6650., "fallback (B200_PROFILING.md)"
 
 
+def traffic_from_profile(args):
+  """DRAM bytes (read + written) of ONE numerator launch at the bench size, from the committed ncu --set full
+  capture of this same command (profiles/traffic.json, written by scripts/ncu_traffic.py); None when the
+  capture does not match the running configuration."""
+  p = os.path.join(ROOT, "profiles", "traffic.json")
+  if not os.path.exists(p):
+    return None
+  with open(p) as f:
+    d = json.load(f)
+  same = all(d.get(k) == getattr(args, k) for k in ("nev", "ns", "nz", "hyper_side")) and d.get("fp_mode") == args.fp_mode
+  return d.get("dram_bytes_per_launch") if same else None
+
+
 # ------------------------------------------------------------------------------------------ arms
 def run_reference(args, rank, world):
   """CPU arm: the oracle restatement of the reference on all host cores, bounded sample."""
@@ -238,7 +251,17 @@ def run_ours(args, rank, world, local_rank):
   torch.cuda.set_device(local_rank)
   dev = torch.device("cuda", local_rank)
   w = build_workload(args, rank)
+  # cold start: handle creation + one-time upload of every input from host buffers + the first evaluation
+  torch.cuda.synchronize()
+  t_cold = time.perf_counter()
   like = build_likelihood(w, args.fp_mode, distributed=world > 1)
+  like(**w["hyper"])
+  torch.cuda.synchronize()
+  cold_s = time.perf_counter() - t_cold
+  ev_keys = ("m1det", "m2det", "dL", "pe_prior", "ra", "dec", "pixels_opt_nsides", "ra_pix", "dec_pix", "gw_loc2d_pdf",
+             "pixels_pe_opt_nside")
+  cold_bytes = int(sum(np.asarray(w["ev"][k]).nbytes for k in ev_keys) + w["zg"].nbytes + w["p_cat"].nbytes
+                   + w["P_compl"].nbytes + sum(v.nbytes for v in w["inj"].values()))
   rows, _ = like.population.update(**w["hyper"]).hyper_rows()
   n_hyper = rows.shape[0]
   nev_local = w["ev"]["dL"].shape[0]
@@ -312,12 +335,13 @@ def run_ours(args, rank, world, local_rank):
     "dtype": "f32" if args.fp_mode == "fp32" else "f64", "data": "synthetic",
     "config": {"workload": WORKLOAD, "events_per_gpu": nev_local, "samples_per_event": args.ns,
                "injections_per_gpu": args.ninj, "n_hyper": n_hyper, "z_int_res": args.nz,
-               "fp_mode": args.fp_mode + " KDE pair sums; fp64 reweighting, tables, z-integral, selection",
+               "fp_mode": (args.fp_mode + ": fp32 reweighting + KDE pair sums (MUFU), fp64 tables/statistics/z-integral/reductions"
+                           if args.fp_mode == "fp32" else "fp64 throughout"),
                "l2": "inputs larger than L2 (160 MB samples + 36 MB p_cat + 32 MB injections per GPU), no flush",
                "p_cat": "smooth synthetic catalogue term (synth.smooth_p_cat), same layout/sentinels",
                "step": "all hyper-points x (all events + all injections) + all-reduce of (n_hyper,3) partials"},
-    "roofline": {"bound": "mufu_fp32_exp", "kernel": "numerator_kernel", "achieved": achieved, "peak": float(peak[0]) / 1e9,
-                 "unit": "Gexp/s", "frac": achieved / (float(peak[0]) / 1e9), "traffic": None,
+    "roofline": {"bound": "mufu_fp32_exp", "kernel": "numerator_f32_kernel<0>" if args.fp_mode == "fp32" else "numerator_kernel", "achieved": achieved, "peak": float(peak[0]) / 1e9,
+                 "unit": "Gexp/s", "frac": achieved / (float(peak[0]) / 1e9), "traffic": traffic_from_profile(args),
                  "algorithmic": f"G*Ns exps per unit = {G}*{args.ns}; x {nev_local * n_hyper} units per launch",
                  "kernel_ms": num_ms, "peak_source": "ex2.approx micro-benchmark measured in this run (chb_mufu_peak)",
                  "nominal_peak": nominal},
@@ -328,22 +352,25 @@ def run_ours(args, rank, world, local_rank):
     "kernel_ms": {k: float(v) for k, v in kt.items()},
     "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(rows.nbytes), "d2h_bytes_per_step": int(n_hyper * 3 * 8),
             "call": "hyperlikelihood.__call__(H0=array, Om0=array) -> chb_eval (host buffers) -> chb_finalize"},
+    "e2e_cold": {"seconds": cold_s, "h2d_bytes": cold_bytes,
+                 "what": "hyperlikelihood(...) construction (chb_create, chb_set_events/pixels/catalog/injections from host "
+                         "buffers, host-side sort + packing) + the first __call__; paid once per run, as in the reference"},
     "gpu_launches": int(launches), "clocks": clocks,
   }
   if world == 1 and not args.no_cpu_baseline:
     procs = 1
-    r = cpu_oracle_rate(w, n_events=24, n_hyper=4, procs=procs)
+    r = cpu_oracle_rate(w, n_events=160, n_hyper=8, procs=procs)
     line["cpu_baseline"] = {"value": r["rate"], "unit": UNIT, "cores": procs, "kind": "port",
-                            "sample": f"{r['n_events']} events x 4 hyper-points + full {args.ninj} injections x 4 hyper-points "
+                            "sample": f"{r['n_events']} events x 8 hyper-points + full {args.ninj} injections x 8 hyper-points "
                                       f"({r['seconds']:.1f} s of CPU work); value = Nev/(Nev*t_unit+t_sel)",
                             "t_unit_ms": 1e3 * r["t_unit"], "t_sel_s": r["t_sel"]}
     # cross-check of the timed configuration against the oracle on the sampled units
-    idx = np.linspace(0, n_hyper - 1, 4).astype(int)
+    idx = np.linspace(0, n_hyper - 1, 8).astype(int)
     lle = like.compute_all(**{k: v[idx] for k, v in w["hyper"].items()})[0][:, :r["n_events"]]
     ref = np.nan_to_num(r["lle"], nan=-np.inf)
     fin = np.isfinite(ref) & (np.abs(ref) < 1e300)
-    line["parity_check"] = {"max_rel_err_vs_oracle": float(np.max(np.abs(lle[fin] - ref[fin]) / np.abs(ref[fin]))),
-                            "units": int(fin.sum())}
+    line["parity_check"] = {"max_err_vs_oracle": float(np.max(np.abs(lle[fin] - ref[fin]) / np.maximum(np.abs(ref[fin]), 1.0))),
+                            "metric": "|d log L| / max(|log L|, 1) per (event, hyper-point)", "units": int(fin.sum())}
   print(json.dumps(line), flush=True)
 
 

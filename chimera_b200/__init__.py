@@ -14,4 +14,5 @@ from .likelihood import hyperlikelihood
 from .selection_function import selection_function
 from . import parallel
 from . import sky
+from . import sampling
 from .sky import pixelize_gw_catalog

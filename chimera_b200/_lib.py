@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libchimera_b200.so")
+LIB_PATH = os.environ.get("CHB_LIB") or os.path.join(_HERE, "libchimera_b200.so")     # CHB_LIB: A/B builds
 
 CHB_ABI_VERSION = 1
 CHB_NPAR = 32

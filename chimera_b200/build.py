@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libchimera_b200.so")
+LIB = os.environ.get("CHB_BUILD_OUT") or os.path.join(HERE, "libchimera_b200.so")
 SOURCES = ["tables.cu", "selection.cu", "numerator.cu", "numerator_f32.cu", "api.cu", "microbench.cu", "setup.cu"]
 # setup.cu holds the HEALPix index arithmetic: no FMA contraction, so that it rounds like the host libraries
 EXTRA_FLAGS = {"setup.cu": ["-fmad=false"]}
@@ -27,12 +27,13 @@ def build(force=False, verbose=False):
   if not force and not _stale():
     return LIB
   nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-  flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+  flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")] + os.environ.get("CHB_BUILD_DEFS", "").split()
   objs = []
-  os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+  bdir = os.path.join(HERE, "build" + ("_" + os.path.basename(LIB) if os.environ.get("CHB_BUILD_OUT") else ""))
+  os.makedirs(bdir, exist_ok=True)
   procs = []
   for s in SOURCES:
-    o = os.path.join(HERE, "build", s.replace(".cu", ".o"))
+    o = os.path.join(bdir, s.replace(".cu", ".o"))
     cmd = [nvcc] + flags + EXTRA_FLAGS.get(s, []) + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, s), "-o", o]
     procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     objs.append(o)

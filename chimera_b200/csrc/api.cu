@@ -61,6 +61,11 @@ struct chb_handle {
   DevBuf<float4> s4;
   DevBuf<float2> l2;
   DevBuf<float2> zterms;
+  DevBuf<float2> zw_stage;
+  DevBuf<double> unit_stats;
+  int64_t plan_nh = -1, plan_nev = -1, plan_ns = -1, plan_nb = 0;
+  int plan_per1 = 0, plan_per2 = 0;
+  bool plan_ok = false;
   DevBuf<double> catA, catB;
   bool cat_collapsed = false;
   bool want_prof = false;
@@ -159,7 +164,7 @@ void chb_destroy(chb_handle* h) {
   for (auto* b : dbl) b->release();
   h->pix_off.release();
   h->prof.release();
-  h->s4.release(); h->l2.release(); h->inj_s4.release(); h->inj_l2.release(); h->zterms.release(); h->catA.release(); h->catB.release();
+  h->s4.release(); h->l2.release(); h->inj_s4.release(); h->inj_l2.release(); h->zterms.release(); h->zw_stage.release(); h->unit_stats.release(); h->catA.release(); h->catB.release();
   h->neff_pix.release();
   for (auto& evn : h->ev) if (evn) cudaEventDestroy(evn);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -393,27 +398,84 @@ static int eval_impl(chb_handle* h, int64_t n_hyper, const double* d_hyper, doub
     a.prof = nullptr;
     bool fast = false;
     if (c.fp_mode == CHB_FP32) {
-      // fast path: 256-thread CTAs, float2 staging; two CTAs per SM when the plan fits in ~113 KB
-      size_t fs = numerator_f32_smem_bytes(a);
-      if (fs <= (size_t)h->max_smem_optin) {
-        CU(numerator_f32_configure(a.kind, fs), "numerator_f32 smem opt-in");
-        int per_sm = numerator_f32_ctas_per_sm(a.kind, fs);
-        if (per_sm >= 1) {
-          int grid = (int)std::min<long long>(units, (long long)h->sm_count * per_sm);
-          h->num_grid = grid; h->num_smem = fs;
-          if (h->want_prof) { CU(h->prof.alloc((size_t)grid * 8), "alloc profile"); a.prof = h->prof.p; }
-          // z-grid terms for all (hyper-point, event, k) in one full-occupancy pass when they fit in 2 GiB
-          const size_t zt_elems = (size_t)n_hyper * h->Nev * h->Nz;
-          a.zterms = nullptr; a.zterms_out = nullptr; a.zterms_h0 = 0;
-          if (zt_elems * sizeof(float2) <= ((size_t)2 << 30)) {
-            CU(h->zterms.alloc(zt_elems), "alloc z-grid terms");
-            a.zterms_out = h->zterms.p;
-            CU(launch_zgrid_terms(a, 0, (int)n_hyper, s), "zgrid_terms launch");
-            h->launches++;
-            a.zterms = h->zterms.p;
+      // fast path: 256-thread CTAs, float2 staging.  Split form (default): reweighting kernel -> stage buffers in
+      // global memory -> KDE/z-integral kernel, three CTAs per SM each; fused form (CHB_SPLIT=0, odd Ns, or no
+      // memory for the stage): one kernel, two CTAs per SM.
+      size_t fs = numerator_f32_smem_bytes(a, 0);
+      const size_t fs1 = numerator_f32_smem_bytes(a, 1), fs2 = numerator_f32_smem_bytes(a, 2);
+      bool split = (h->Ns % 2 == 0) && fs2 <= (size_t)h->max_smem_optin && fs1 <= (size_t)h->max_smem_optin;
+      { const char* e = getenv("CHB_SPLIT"); if (e && e[0] == '0') split = false; }
+      int64_t nb = n_hyper;                        // hyper-points per batch of the split form
+      if (split) {
+        // the plan (batch size, stage buffers, occupancy) is cached per (n_hyper, Nev, Ns): no driver queries
+        // inside the timed region of later evaluations
+        if (h->plan_nh != n_hyper || h->plan_nev != h->Nev || h->plan_ns != h->Ns) {
+          size_t budget = (size_t)12 << 30;
+          { const char* e = getenv("CHB_STAGE_GB"); if (e && atof(e) > 0) budget = (size_t)(atof(e) * (double)((size_t)1 << 30)); }
+          const size_t per_h = (size_t)h->Nev * h->Ns * sizeof(float2);
+          nb = std::max<int64_t>(1, std::min<int64_t>(n_hyper, (int64_t)(budget / per_h)));
+          size_t free_b = 0, total_b = 0;
+          cudaMemGetInfo(&free_b, &total_b);
+          while (nb > 1 && h->zw_stage.n < (size_t)nb * h->Nev * h->Ns && (size_t)nb * per_h > free_b / 2) nb = (nb + 1) / 2;
+          h->plan_ok = false;
+          if (h->zw_stage.alloc((size_t)nb * h->Nev * h->Ns) == cudaSuccess &&
+              h->unit_stats.alloc((size_t)nb * h->Nev * 8) == cudaSuccess &&
+              numerator_f32_configure(a.kind, 1, fs1) == cudaSuccess && numerator_f32_configure(a.kind, 2, fs2) == cudaSuccess) {
+            h->plan_per1 = numerator_f32_ctas_per_sm(a.kind, 1, fs1);
+            h->plan_per2 = numerator_f32_ctas_per_sm(a.kind, 2, fs2);
+            h->plan_ok = h->plan_per1 >= 1 && h->plan_per2 >= 1;
           }
-          CU(launch_numerator_f32(a, grid, fs, s), "numerator_f32 launch");
+          cudaGetLastError();
+          h->plan_nb = nb; h->plan_nh = n_hyper; h->plan_nev = h->Nev; h->plan_ns = h->Ns;
+        }
+        nb = h->plan_nb;
+        split = h->plan_ok;
+      }
+      if (split || fs <= (size_t)h->max_smem_optin) {
+        // z-grid terms for all (hyper-point, event, k) in one full-occupancy pass when they fit in 2 GiB
+        const size_t zt_elems = (size_t)n_hyper * h->Nev * h->Nz;
+        a.zterms = nullptr; a.zterms_out = nullptr; a.zterms_h0 = 0;
+        if (zt_elems * sizeof(float2) <= ((size_t)2 << 30)) {
+          CU(h->zterms.alloc(zt_elems), "alloc z-grid terms");
+          a.zterms_out = h->zterms.p;
+          CU(launch_zgrid_terms(a, 0, (int)n_hyper, s), "zgrid_terms launch");
+          h->launches++;
+          a.zterms = h->zterms.p;
+        }
+        if (split) {
+          const int per1 = h->plan_per1, per2 = h->plan_per2;
+          h->num_smem = fs2;
+          for (int64_t h0 = 0; h0 < n_hyper; h0 += nb) {
+            const int64_t nh = std::min<int64_t>(nb, n_hyper - h0);
+            NumArgs b = a;                         // this batch: pointers shifted to hyper-point h0
+            b.n_hyper = (int)nh;
+            b.hyper = a.hyper + (size_t)h0 * CHB_NPAR; b.tabs = a.tabs + (size_t)h0 * a.mc.lay.total(); b.HC = a.HC + (size_t)h0 * CHB_NHC;
+            b.log_like = a.log_like + (size_t)h0 * h->Nev; b.like_raw = a.like_raw + (size_t)h0 * h->Nev;
+            if (a.p_gw_out) b.p_gw_out = a.p_gw_out + (size_t)h0 * h->Nev * (size_t)(c.kind_p_gw == CHB_PGW_1D ? 1 : a.P) * h->Nz;
+            if (a.zterms) b.zterms = a.zterms + (size_t)h0 * h->Nev * h->Nz;
+            b.zw_stage = h->zw_stage.p; b.unit_stats = h->unit_stats.p;
+            const long long ub = (long long)h->Nev * nh;
+            const int g1 = (int)std::min<long long>(ub, (long long)h->sm_count * per1);
+            const int g2 = (int)std::min<long long>(ub, (long long)h->sm_count * per2);
+            h->num_grid = g2;
+            b.prof = nullptr;
+            CU(launch_numerator_f32(b, 1, g1, fs1, s), "reweight_f32 launch");
+            if (h->want_prof) { CU(h->prof.alloc((size_t)g2 * 8), "alloc profile"); b.prof = h->prof.p; }
+            CU(launch_numerator_f32(b, 2, g2, fs2, s), "kde_f32 launch");
+            h->launches += 2;
+          }
+          h->launches--;                           // the common `launches++` below counts one of them
           fast = true;
+        } else {
+          CU(numerator_f32_configure(a.kind, 0, fs), "numerator_f32 smem opt-in");
+          int per_sm = numerator_f32_ctas_per_sm(a.kind, 0, fs);
+          if (per_sm >= 1) {
+            int grid = (int)std::min<long long>(units, (long long)h->sm_count * per_sm);
+            h->num_grid = grid; h->num_smem = fs;
+            if (h->want_prof) { CU(h->prof.alloc((size_t)grid * 8), "alloc profile"); a.prof = h->prof.p; }
+            CU(launch_numerator_f32(a, 0, grid, fs, s), "numerator_f32 launch");
+            fast = true;
+          }
         }
       }
     }

@@ -44,6 +44,10 @@ struct NumArgs {
   double* p_gw_out;      // optional (n_hyper, Nev, [P,] Nz)
   // fp32 fast path: precomputed z-grid terms {dVc/dz, ck} for hyper-points [zterms_h0, zterms_h0 + n)
   const float2* zterms;
+  // split fast path (numerator_f32_kernel MODE 1 -> MODE 2): reweighted samples {z, w} (units x Ns) and the unit
+  // statistics {sum w, sum w^2, min z, max z, std z, -, -, -} (units x 8), unit = ev * n_hyper + h
+  float2* zw_stage;
+  double* unit_stats;
   float2* zterms_out;
   int zterms_h0;
   // optional phase profile: (gridDim, 8) SM-clock cycles accumulated by thread 0 of every CTA
@@ -73,10 +77,10 @@ size_t numerator_smem_bytes(const NumArgs& a, bool stage_in_smem);
 long long numerator_scratch_doubles(const NumArgs& a);
 int numerator_block_threads();
 cudaError_t numerator_configure(size_t smem);
-size_t numerator_f32_smem_bytes(const NumArgs& a);
-cudaError_t numerator_f32_configure(int kind, size_t smem);
-int numerator_f32_ctas_per_sm(int kind, size_t smem);
-cudaError_t launch_numerator_f32(const NumArgs& a, int grid, size_t smem, cudaStream_t s);
+size_t numerator_f32_smem_bytes(const NumArgs& a, int mode);
+cudaError_t numerator_f32_configure(int kind, int mode, size_t smem);
+int numerator_f32_ctas_per_sm(int kind, int mode, size_t smem);
+cudaError_t launch_numerator_f32(const NumArgs& a, int mode, int grid, size_t smem, cudaStream_t s);
 cudaError_t launch_zgrid_terms(const NumArgs& a, int h0, int nh, cudaStream_t s);
 cudaError_t launch_catalog_collapse(int Nev, int P, int Nz, const double* p_cat, const double* gw_pdf, const int* neff_pix,
                                    double* catA, double* catB, cudaStream_t s);

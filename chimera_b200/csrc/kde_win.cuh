@@ -59,9 +59,11 @@ __device__ __forceinline__ bool win_plan(int G, int n, float h, int iters, int m
     }
   }
   if (pl.R == 0) return false;
-  pl.chunk = iters * (32 / pl.LPS);
-  while ((n + pl.chunk - 1) / pl.chunk > max_chunks) pl.chunk *= 2;
+  // at most 32 chunks (phase B keeps one chunk per lane), each a multiple of 4 sub-stream rounds
+  const int q = 4 * (32 / pl.LPS);
+  pl.chunk = max(iters * (32 / pl.LPS), ((n + 31) / 32 + q - 1) / q * q);
   pl.nchunks = (n + pl.chunk - 1) / pl.chunk;
+  (void)max_chunks;
   return pl.nchunks >= 8;
 }
 
@@ -149,40 +151,39 @@ __device__ __forceinline__ void kde_win_pass(const float2* __restrict__ xl, int 
   }
 }
 
-// Phase C driver: the passes of all chunks form one list (pend[c] = inclusive prefix sum of passes per chunk,
-// kept in the .w slot of the chunk table); warp w takes the contiguous slice [w T/NW, (w+1) T/NW) of it, so the
-// extra passes of the wide edge chunks are spread over the warps and the split is the same on every run.
+// Phase C driver: the passes of all chunks form one list; lane c of every warp holds chunk c's window and the
+// inclusive prefix sum of passes (pend), so a warp finds the chunk of list item `it` with one ballot.  Warp w
+// takes the contiguous slice [w T/NW, (w+1) T/NW) of the list: the extra passes of the wide edge chunks are
+// spread over the warps and the split is the same on every run (bit-reproducible sums).
 template <int R, int LPS, int NW>
 __device__ __forceinline__ void kde_win_chunks(const float2* __restrict__ xl, int n, int G, double gfirst, double hd,
-                                               const WinPlan& pl, const float4* __restrict__ summ,
-                                               const int2* __restrict__ win, int total, const float* __restrict__ cr,
-                                               double* __restrict__ rows) {
+                                               const WinPlan& pl, const float4* __restrict__ summ, int2 w, int np,
+                                               int pend, const float* __restrict__ cr, double* __restrict__ rows) {
   constexpr int W = LPS * R;
   const int warp = threadIdx.x >> 5;
   const float h = (float)hd;
   double* row = rows + warp * G;
+  const int total = __shfl_sync(0xffffffffu, pend, 31);
   const int i0 = (int)(((long long)warp * total) / NW), i1 = (int)(((long long)(warp + 1) * total) / NW);
-  int c = 0;
   for (int it = i0; it < i1; ++it) {
-    while (it >= __float_as_int(summ[c].w)) ++c;
-    const int2 w = win[c];
-    const int np = (w.y - w.x + W) / W;
-    const int gb = w.x + (it - (__float_as_int(summ[c].w) - np)) * W;
+    const int c = __popc(__ballot_sync(0xffffffffu, pend <= it));      // first chunk whose prefix exceeds `it`
+    const int wx = __shfl_sync(0xffffffffu, w.x, c), wy = __shfl_sync(0xffffffffu, w.y, c);
+    const int first = __shfl_sync(0xffffffffu, pend - np, c);
+    const int gb = wx + (it - first) * W;
     const int cb = c * pl.chunk, ce = min(n, cb + pl.chunk);
-    kde_win_pass<R, LPS>(xl, cb, ce, gb, w.y, summ[c], gfirst, hd, h, cr, row);
+    kde_win_pass<R, LPS>(xl, cb, ce, gb, wy, summ[c], gfirst, hd, h, cr, row);
     __syncwarp();
   }
 }
 
 // Whole-CTA call (NW warps).  xw: in {x, w} (x sorted or not), out {x', log2 w'}.  Scratch: summ/win hold
-// pl.nchunks entries, cr 16 floats + 1 int, rows NW*G doubles.  dens[g] = scale * sum_j w'_j 2^-(g'_g - x'_j)^2 with
+// pl.nchunks (<= 32) entries, cr 16 floats, rows NW*G doubles.  dens[g] = scale * sum_j w'_j 2^-(g'_g - x'_j)^2 with
 // g'_g = (lb + g step - c) sf, sf = float(s) shared by samples and grid.
 template <int NW>
 __device__ __forceinline__ void kde1d_f32_win(float2* __restrict__ xw, int n, int G, double lb, double step, double c,
                                               double s, double W, const WinPlan& pl, double scale,
                                               float4* __restrict__ summ, int2* __restrict__ win, float* __restrict__ cr,
                                               double* __restrict__ rows, double* __restrict__ dens) {
-  int* total_passes = reinterpret_cast<int*>(cr + 16);                 // cr: 16 floats + 1 int of scratch
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float sf = (float)s;
   const double gfirst = (lb - c) * (double)sf, hd = step * (double)sf;
@@ -215,48 +216,31 @@ __device__ __forceinline__ void kde1d_f32_win(float2* __restrict__ xw, int n, in
     }
   }
   __syncthreads();
-  // ---- phase B: per grid point the lower bound M(g); per chunk the hull of the points it can matter at ----
+  // ---- phase B: lane c holds chunk c; every warp walks its share of the grid points: M(g) is one warp-wide max,
+  // the need test one compare per lane, the hull of the needed points accumulates in registers ------------
   const float lgchunk = lg2f_((float)pl.chunk);
-  for (int gbase = warp * 32; gbase < G; gbase += NW * 32) {
-    const int g = gbase + lane;
-    const float gp = (float)(gfirst + (double)g * hd);
-    float m = -INFINITY;
-    for (int ck = 0; ck < pl.nchunks; ++ck) {
-      const float4 s4 = summ[ck];
-      const float d = gp - s4.w;
-      m = fmaxf(m, fmaf(-d, d, s4.z));
+  const float4 my = (lane < pl.nchunks) ? summ[lane] : make_float4(INFINITY, -INFINITY, -INFINITY, 0.f);
+  {
+    const float myU = my.z + lgchunk, gf = (float)gfirst;
+    int gmin = G, gmax = -1;
+    for (int g = warp; g < G; g += NW) {
+      const float gp = fmaf((float)g, h, gf);
+      const float d = gp - my.w;
+      const float m = warp_max_f32(fmaf(-d, d, my.z));
+      const float dist = fmaxf(fmaxf(my.x - gp, gp - my.y), 0.f);
+      if (fmaf(-dist, dist, myU) >= m - CHB_WIN_T2 && my.z > -INFINITY) { gmin = min(gmin, g); gmax = g; }
     }
-    const float thr = m - CHB_WIN_T2;
-    for (int ck = 0; ck < pl.nchunks; ++ck) {
-      const float4 s4 = summ[ck];
-      const float dist = fmaxf(fmaxf(s4.x - gp, gp - s4.y), 0.f);
-      const bool need = (g < G) && (s4.z > -INFINITY) && (fmaf(-dist, dist, s4.z + lgchunk) >= thr);
-      const unsigned b = __ballot_sync(0xffffffffu, need);
-      if (b && lane == 0) {
-        atomicMin(&win[ck].x, gbase + __ffs(b) - 1);
-        atomicMax(&win[ck].y, gbase + 31 - __clz(b));
-      }
-    }
+    if (gmax >= 0) { atomicMin(&win[lane].x, gmin); atomicMax(&win[lane].y, gmax); }
   }
   __syncthreads();
   // ---- phase C: pair sums ------------------------------------------------------------------------
-  if (warp == 0) {                                                     // passes per chunk -> inclusive prefix sums
-    const int W = pl.LPS * pl.R;
-    int carry = 0;
-    for (int base = 0; base < pl.nchunks; base += 32) {
-      const int ck = base + lane;
-      int x = 0;
-      if (ck < pl.nchunks) { const int2 w = win[ck]; x = (w.x <= w.y) ? (w.y - w.x + W) / W : 0; }
+  const int Wp = pl.LPS * pl.R;
+  const int2 w = (lane < pl.nchunks) ? win[lane] : make_int2(G, -1);
+  const int np = (w.x <= w.y) ? (w.y - w.x + Wp) / Wp : 0;
+  int pend = np;                                                       // inclusive prefix sum of passes per chunk
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-      if (ck < pl.nchunks) summ[ck].w = __int_as_float(carry + x);
-      carry += __shfl_sync(0xffffffffu, x, 31);
-    }
-    if (lane == 0) *total_passes = carry;
-  }
-  __syncthreads();
-  const int total = *total_passes;
-#define CHB_WIN_CASE(RR, LL) case RR * 16 + LL: kde_win_chunks<RR, LL, NW>(xw, n, G, gfirst, hd, pl, summ, win, total, cr, rows); break;
+  for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, pend, o); if (lane >= o) pend += y; }
+#define CHB_WIN_CASE(RR, LL) case RR * 16 + LL: kde_win_chunks<RR, LL, NW>(xw, n, G, gfirst, hd, pl, summ, w, np, pend, cr, rows); break;
   switch (pl.R * 16 + pl.LPS) {
     CHB_WIN_CASE(4, 2) CHB_WIN_CASE(4, 4) CHB_WIN_CASE(4, 8)
     CHB_WIN_CASE(8, 2) CHB_WIN_CASE(8, 4) CHB_WIN_CASE(8, 8)

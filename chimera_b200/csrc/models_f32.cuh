@@ -139,24 +139,29 @@ __device__ __forceinline__ float smoothing_bf(float m, float dm, float lo) {
   S = (x > dm) ? 1.f : S;
   return (x < 0.f) ? 0.f : S;
 }
+// SMOOTH = false: the caller has checked that every mass is above m_low + delta_m (smoothing == 1 exactly,
+// mass.py:255-264), so the taper is skipped.
+template <bool SMOOTH>
 __device__ __forceinline__ float weight_bf(const F32Consts& c, float m1, float m2, float lg2m1, float lg2m2,
                                            float inv_prior) {
   const bool in1 = (c.lo <= m1) && (m1 <= c.hi);
+  const bool taper = SMOOTH && (c.mass_model != CHB_MASS_TPL);
   float p1;
   if (c.mass_model == CHB_MASS_TPL) {
     p1 = ex2f_(c.neg_alpha * lg2m1);
   } else if (c.mass_model == CHB_MASS_BPL) {
     const float a = (m1 <= c.mb) ? ex2f_(c.neg_alpha * lg2m1) : 0.f;
     const float b = (m1 >= c.mb) ? ex2f_(c.neg_alpha2 * lg2m1) * c.ratio : 0.f;
-    p1 = (a + b) * smoothing_bf(m1, c.dm, c.lo);
+    p1 = a + b;
   } else {
     const float Ppl = ex2f_(c.neg_alpha * lg2m1) * c.inv_plnorm;
     const float d = m1 - c.mu;
     const float G = (m1 <= c.g_hi) ? ex2f_(c.g_c * d * d) * c.g_pref : 0.f;
-    p1 = ((1.f - c.lam) * Ppl + c.lam * G) * smoothing_bf(m1, c.dm, c.lo);
+    p1 = (1.f - c.lam) * Ppl + c.lam * G;
   }
+  if (taper) p1 *= smoothing_bf(m1, c.dm, c.lo);
   float p2 = ex2f_(c.beta * lg2m2);
-  if (c.mass_model != CHB_MASS_TPL) p2 *= smoothing_bf(m2, c.dm, c.lo);
+  if (taper) p2 *= smoothing_bf(m2, c.dm, c.lo);
   int i = (int)((lg2m1 - c.lg2_m0) * c.inv_lg2_mstep);
   i = max(0, min(i, c.rm - 2));
   const float4 e = c.cd4[i];

@@ -23,14 +23,31 @@
 
 #define F_NT 256
 #define F_NW (F_NT / 32)
+// tuning knobs of the split fast path (build.py passes -D overrides from CHB_BUILD_DEFS for A/B runs)
+#ifndef CHB_K1_MINB
+#define CHB_K1_MINB 3        // co-resident CTAs per SM the reweighting kernel (MODE 1) is compiled for
+#endif
+#ifndef CHB_K1_U
+#define CHB_K1_U 2           // samples in flight per thread in the reweighting loop (x2 with the prefetch)
+#endif
+#ifndef CHB_K2_MINB
+#define CHB_K2_MINB 3        // co-resident CTAs per SM of the KDE/z-integral kernel (MODE 2)
+#endif
 
 struct FPlan {
   int tab, zgrid, dV, ck, pgw, eg, dens, bc, bs, xwb, part, red, stage, total;
 };
-__host__ __device__ inline FPlan make_fplan(int tab_doubles, int Nz, int B, int Ns, int kind) {
+// mode 0: fused kernel; 1: reweighting only (table + reduction scratch); 2: KDE + z-integral on staged samples (no table)
+__host__ __device__ inline FPlan make_fplan(int tab_doubles, int Nz, int B, int Ns, int kind, int mode = 0) {
   FPlan p;
   int o = 0;
-  p.tab = o; o += tab_doubles;
+  p.tab = o; o += (mode == 2) ? 0 : tab_doubles;
+  if (mode == 1) {
+    p.zgrid = p.dV = p.ck = p.eg = p.pgw = p.dens = p.bc = p.bs = p.xwb = p.part = o;
+    p.red = o; o += 64;
+    p.stage = o; p.total = o;
+    return p;
+  }
   p.zgrid = o; o += Nz;
   p.dV = o; o += Nz;
   p.ck = o; o += Nz;
@@ -49,8 +66,8 @@ __host__ __device__ inline FPlan make_fplan(int tab_doubles, int Nz, int B, int 
 }
 static inline int f32_tab_doubles(const TableLayout& lay) { return lay.f32_total() - lay.f32_dl4(); }
 
-size_t numerator_f32_smem_bytes(const NumArgs& a) {
-  return (size_t)make_fplan(f32_tab_doubles(a.mc.lay), a.Nz, a.binning ? a.num_bins : 0, a.Ns, a.kind).total * sizeof(double);
+size_t numerator_f32_smem_bytes(const NumArgs& a, int mode) {
+  return (size_t)make_fplan(f32_tab_doubles(a.mc.lay), a.Nz, a.binning ? a.num_bins : 0, a.Ns, a.kind, mode).total * sizeof(double);
 }
 
 __device__ __forceinline__ double nan_to_num_log_f(double like) {
@@ -173,8 +190,12 @@ cudaError_t launch_zgrid_terms(const NumArgs& a, int h0, int nh, cudaStream_t s)
 
 // KG: kind group the kernel is compiled for (0: '1d'/'approximate', 1: 'marginalized', 2: 'full') -- one
 // instantiation per group keeps the instruction footprint of the hot 1-D path small.
-template <int KG>
-__global__ void __launch_bounds__(F_NT, 2)
+// MODE: 0 = fused (reweighting + KDE + z-integral per unit in one CTA pass); 1 = reweighting + statistics only,
+// samples {z, w} and the unit statistics go to the stage buffers in global memory; 2 = KDE + z-integral on the
+// staged samples of a unit (one TMA bulk copy into shared memory).  Splitting lets either half run with three
+// co-resident CTAs per SM (no 42 KB table block next to the 40 KB sample stage) -- see DESIGN.md section 4.
+template <int KG, int MODE>
+__global__ void __launch_bounds__(F_NT, MODE == 0 ? 2 : (MODE == 1 ? CHB_K1_MINB : CHB_K2_MINB))
 numerator_f32_kernel(const NumArgs a) {
   extern __shared__ __align__(16) double sm[];
   __shared__ __align__(8) uint64_t bar;
@@ -183,11 +204,14 @@ numerator_f32_kernel(const NumArgs a) {
   __shared__ double L[8];
   __shared__ int next_chunk;
   __shared__ float crs[20];
+  __shared__ double sh_bw;
+  __shared__ WinPlan sh_wp;
+  __shared__ int sh_win;
 
   const TableLayout lay = a.mc.lay;
   const int Ns = a.Ns, Nz = a.Nz, Pp = a.P, B = a.binning ? a.num_bins : 0;
   const int tabd = lay.f32_total() - lay.f32_dl4();
-  const FPlan pl = make_fplan(tabd, Nz, B, Ns, a.kind);
+  const FPlan pl = make_fplan(tabd, Nz, B, Ns, a.kind, MODE);
   double* tab = sm + pl.tab;
   double* zgrid = sm + pl.zgrid;
   double* dV = sm + pl.dV;
@@ -200,7 +224,7 @@ numerator_f32_kernel(const NumArgs a) {
   float2* xwb = reinterpret_cast<float2*>(sm + pl.xwb);
   float* part = reinterpret_cast<float*>(sm + pl.part);
   double* red = sm + pl.red;
-  float2* zw = reinterpret_cast<float2*>(sm + pl.stage);
+  float2* zw_s = reinterpret_cast<float2*>(sm + pl.stage);
   float4* yw = reinterpret_cast<float4*>(sm + pl.stage + Ns);      // 'full' only
 
   const int cm = a.mc.cosmo_model;
@@ -220,20 +244,28 @@ numerator_f32_kernel(const NumArgs a) {
     const int ev = (int)(unit / a.n_hyper), h = (int)(unit % a.n_hyper);
     __syncthreads();
     const double* tblk = a.tabs + (size_t)h * lay.total() + lay.off_f32();
+    float2* zw = (MODE == 1) ? a.zw_stage + (size_t)unit * Ns : zw_s;
     if (tid == 0) {
       fence_proxy_async();
-      mbar_expect_tx(&bar, tab_bytes);
-      bulk_g2s(tab, tblk + lay.f32_dl4(), tab_bytes, &bar);
+      if (MODE != 2) {
+        mbar_expect_tx(&bar, tab_bytes);
+        bulk_g2s(tab, tblk + lay.f32_dl4(), tab_bytes, &bar);
+      } else {
+        mbar_expect_tx(&bar, (uint32_t)(Ns * sizeof(float2)));
+        bulk_g2s(zw_s, a.zw_stage + (size_t)unit * Ns, (uint32_t)(Ns * sizeof(float2)), &bar);
+      }
     }
     if (tid < CHB_NPAR) P[tid] = a.hyper[(size_t)h * CHB_NPAR + tid];
     if (tid >= 64 && tid < 64 + CHB_NHC) HC[tid - 64] = a.HC[(size_t)h * CHB_NHC + tid - 64];
     if (tid == 128) next_chunk = 0;
-    const double* zgr = a.zgrids + (size_t)ev * Nz;
-    for (int k = tid; k < Nz; k += F_NT) zgrid[k] = zgr[k];
+    if (MODE != 1) {
+      const double* zgr = a.zgrids + (size_t)ev * Nz;
+      for (int k = tid; k < Nz; k += F_NT) zgrid[k] = zgr[k];
+    }
     __syncthreads();
 
-    // constants of the fast path; table pointers: dl4|cd4|lut in shared memory, zi4 in L2
-    F32Consts fc = make_f32_consts(a.mc, P, HC, tab - lay.f32_dl4());
+    // constants of the fast path; table pointers: dl4|cd4|lut in shared memory (global in MODE 2), zi4 in L2
+    F32Consts fc = make_f32_consts(a.mc, P, HC, (MODE == 2) ? tblk : tab - lay.f32_dl4());
     fc.zi4 = reinterpret_cast<const float4*>(tblk + lay.f32_zi4());
     const CosmoRateF32 cr = make_cosmo_rate_f32(a.mc, P, HC);
     const float z_top = (float)P[CHB_P_ZMAX];
@@ -241,87 +273,130 @@ numerator_f32_kernel(const NumArgs a) {
 
     // ---- z-grid terms: precomputed for all (hyper-point, event, k) by zgrid_terms_kernel when the
     // buffer fits (a.zterms), otherwise evaluated here --------------------------------------------
-    if (a.zterms) {
-      const float2* zt = a.zterms + ((size_t)(h - a.zterms_h0) * a.Nev + ev) * Nz;
-      for (int k = tid; k < Nz; k += F_NT) { const float2 v = __ldg(zt + k); dV[k] = (double)v.x; ck[k] = (double)v.y; }
-    } else {
-      for (int k = tid; k < Nz; k += F_NT) {
-        const double z = zgrid[k];
-        const double zl = (k > 0) ? zgrid[k - 1] : z, zr = (k < Nz - 1) ? zgrid[k + 1] : z;
-        const float2 v = zgrid_terms_f32(fc, cr, P, HC, cm, z, 0.5 * (zr - zl));
-        dV[k] = (double)v.x; ck[k] = (double)v.y;
+    if (MODE != 1) {
+      if (a.zterms) {
+        const float2* zt = a.zterms + ((size_t)(h - a.zterms_h0) * a.Nev + ev) * Nz;
+        for (int k = tid; k < Nz; k += F_NT) { const float2 v = __ldg(zt + k); dV[k] = (double)v.x; ck[k] = (double)v.y; }
+      } else {
+        for (int k = tid; k < Nz; k += F_NT) {
+          const double z = zgrid[k];
+          const double zl = (k > 0) ? zgrid[k - 1] : z, zr = (k < Nz - 1) ? zgrid[k + 1] : z;
+          const float2 v = zgrid_terms_f32(fc, cr, P, HC, cm, z, 0.5 * (zr - zl));
+          dV[k] = (double)v.x; ck[k] = (double)v.y;
+        }
       }
     }
     FPHASE(1);
     mbar_wait(&bar, phase);
     phase ^= 1;
-    fc.cd4_last = fc.cd4[fc.rm - 1];
     FPHASE(0);
 
-    // ---- stage 1: reweighting (pop_wrapper.py:67-80) ------------------------------------------
     const size_t so = (size_t)ev * Ns;
-    Stats6 st = {0.0, 0.0, 0.0, 0.0, INFINITY, -INFINITY};
-    // per-thread partial statistics in fp32 (a thread sees ~Ns/256 samples), z shifted by the redshift of the
-    // event's median-dL sample so that the one-pass variance does not cancel; fp64 from the block reduction on
-    float fa = 0.f, fb = 0.f, fcs = 0.f, fd = 0.f;
-    const float z0 = z_from_dL_f32(fc, __ldg(&a.s4[(size_t)ev * Ns + Ns / 2].x));
-    {
-      // four samples in flight per thread, identical instruction stream for all of them (branch-free
-      // weights, fixed two-step table scan) so the compiler interleaves their dependency chains
-      const float4* s4 = a.s4 + so;
-      const float2* l2 = a.l2 + so;
-      constexpr int U = 4;
-      for (;;) {
+    double s1, s2, zmn, zmx, zstd;
+    if (MODE != 2) {
+      fc.cd4_last = fc.cd4[fc.rm - 1];
+      // ---- stage 1: reweighting (pop_wrapper.py:67-80) ------------------------------------------
+      Stats6 st = {0.0, 0.0, 0.0, 0.0, INFINITY, -INFINITY};
+      // per-thread partial statistics in fp32 (a thread sees ~Ns/256 samples), z shifted by the redshift of the
+      // event's median-dL sample so that the one-pass variance does not cancel; fp64 from the block reduction on
+      float fa = 0.f, fb = 0.f, fcs = 0.f, fd = 0.f;
+      const float z0 = z_from_dL_f32(fc, __ldg(&a.s4[(size_t)ev * Ns + Ns / 2].x));
+      {
+        // four samples in flight per thread, identical instruction stream for all of them (branch-free
+        // weights, fixed two-step table scan) so the compiler interleaves their dependency chains
+        const float4* s4 = a.s4 + so;
+        const float2* l2 = a.l2 + so;
+        constexpr int U = (MODE == 1) ? CHB_K1_U : 2;
+        // software pipeline: the packed samples of the NEXT chunk are requested before the current chunk is
+        // evaluated, so the L2 latency of the loads overlaps ~350 instructions of arithmetic
+        float4 sv[U], nsv[U]; float2 lv[U], nlv[U];
         int cbase = 0;
-        if (lane == 0) cbase = atomicAdd(&next_chunk, U * 32);     // warps pull 128-sample chunks (warp 0 joins late)
+        if (lane == 0) cbase = atomicAdd(&next_chunk, U * 32);     // warps pull U*32-sample chunks
         cbase = __shfl_sync(0xffffffffu, cbase, 0);
-        if (cbase >= Ns) break;
-        const int jb = cbase + lane;
-        float4 sv[U]; float2 lv[U]; float zf[U], wf[U];
-        int kk[U]; float4 ee[U]; bool more[U];
+        if (cbase < Ns) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int j = min(jb + u * 32, Ns - 1);            // tail lanes recompute the last sample, never stored
-          sv[u] = __ldg(s4 + j);
-          lv[u] = __ldg(l2 + j);
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) zf[u] = z_lookup2(fc, sv[u].x, z_top, kk[u], ee[u], more[u]);
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (more[u]) {                                      // rare: keep scanning
-            int k = kk[u]; float4 e = ee[u];
-            while (sv[u].x >= e.w && k < fc.rc - 2) { ++k; e = fc.dl4[k]; }
-            float z = fmaf(sv[u].x - e.x, e.z, e.y);
-            zf[u] = (sv[u].x >= e.w) ? z_top : z;
+          for (int u = 0; u < U; ++u) {
+            const int j = min(cbase + lane + u * 32, Ns - 1);   // tail lanes recompute the last sample, never stored
+            sv[u] = __ldg(s4 + j);
+            lv[u] = __ldg(l2 + j);
           }
         }
+        while (cbase < Ns) {
+          int nbase = 0;
+          if (lane == 0) nbase = atomicAdd(&next_chunk, U * 32);
+          nbase = __shfl_sync(0xffffffffu, nbase, 0);
+          if (nbase < Ns) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const float opz = 1.f + zf[u];
-          const float r = rcpf_(opz), lz = lg2f_(opz);
-          wf[u] = weight_bf(fc, sv[u].y * r, sv[u].z * r, lv[u].x - lz, lv[u].y - lz, sv[u].w);
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int j = jb + u * 32;
-          if (j < Ns) {
-            zw[j] = make_float2(zf[u], wf[u]);
-            const float dz = zf[u] - z0;
-            fa += wf[u]; fb = fmaf(wf[u], wf[u], fb); fcs += dz; fd = fmaf(dz, dz, fd);
-            st.mn = fminf(st.mn, zf[u]); st.mx = fmaxf(st.mx, zf[u]);
+            for (int u = 0; u < U; ++u) {
+              const int j = min(nbase + lane + u * 32, Ns - 1);
+              nsv[u] = __ldg(s4 + j);
+              nlv[u] = __ldg(l2 + j);
+            }
           }
+          const int jb = cbase + lane;
+          float zf[U], wf[U];
+          int kk[U]; float4 ee[U]; bool more[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) zf[u] = z_lookup2(fc, sv[u].x, z_top, kk[u], ee[u], more[u]);
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            if (more[u]) {                                      // rare: keep scanning
+              int k = kk[u]; float4 e = ee[u];
+              while (sv[u].x >= e.w && k < fc.rc - 2) { ++k; e = fc.dl4[k]; }
+              float z = fmaf(sv[u].x - e.x, e.z, e.y);
+              zf[u] = (sv[u].x >= e.w) ? z_top : z;
+            }
+          }
+          float m1s[U], m2s[U], lzs[U];
+          bool smooth = false;                                  // does any sample of the chunk sit on the low-mass taper?
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const float opz = 1.f + zf[u];
+            const float r = rcpf_(opz);
+            lzs[u] = lg2f_(opz);
+            m1s[u] = sv[u].y * r; m2s[u] = sv[u].z * r;
+            smooth |= !(m2s[u] - fc.lo > fc.dm) || !(m1s[u] - fc.lo > fc.dm);
+          }
+          if (__any_sync(0xffffffffu, smooth)) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) wf[u] = weight_bf<true>(fc, m1s[u], m2s[u], lv[u].x - lzs[u], lv[u].y - lzs[u], sv[u].w);
+          } else {                                               // smoothing == 1 for every lane: skip its 6 MUFU per sample
+#pragma unroll
+            for (int u = 0; u < U; ++u) wf[u] = weight_bf<false>(fc, m1s[u], m2s[u], lv[u].x - lzs[u], lv[u].y - lzs[u], sv[u].w);
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int j = jb + u * 32;
+            if (j < Ns) {
+              zw[j] = make_float2(zf[u], wf[u]);
+              const float dz = zf[u] - z0;
+              fa += wf[u]; fb = fmaf(wf[u], wf[u], fb); fcs += dz; fd = fmaf(dz, dz, fd);
+              st.mn = fminf(st.mn, zf[u]); st.mx = fmaxf(st.mx, zf[u]);
+            }
+          }
+          cbase = nbase;
+#pragma unroll
+          for (int u = 0; u < U; ++u) { sv[u] = nsv[u]; lv[u] = nlv[u]; }
         }
       }
+      FPHASE(2);
+      st.a = (double)fa; st.b = (double)fb; st.c = (double)fcs; st.d = (double)fd;
+      st = block_stats(st, red);
+      s1 = st.a; s2 = st.b;
+      zmn = (double)st.mn; zmx = (double)st.mx;
+      const double dzmean = st.c / Ns;
+      zstd = sqrt(fmax(st.d / Ns - dzmean * dzmean, 0.0));    // one-pass variance about z0
+      if (MODE == 1) {
+        if (tid == 0) {
+          double* us = a.unit_stats + (size_t)unit * 8;
+          us[0] = s1; us[1] = s2; us[2] = zmn; us[3] = zmx; us[4] = zstd;
+        }
+        continue;
+      }
+    } else {
+      const double* us = a.unit_stats + (size_t)unit * 8;
+      s1 = us[0]; s2 = us[1]; zmn = us[2]; zmx = us[3]; zstd = us[4];
     }
-    FPHASE(2);
-    st.a = (double)fa; st.b = (double)fb; st.c = (double)fcs; st.d = (double)fd;
-    st = block_stats(st, red);
-    const double s1 = st.a, s2 = st.b;
-    const double zmn = (double)st.mn, zmx = (double)st.mx;
-    const double dzmean = st.c / Ns;
-    const double zstd = sqrt(fmax(st.d / Ns - dzmean * dzmean, 0.0));    // one-pass variance about z0
-    const double zmean = (double)z0 + dzmean;
     const double norm = s1 / Ns;                  // likelihood.py:111
     const double neff = s1 * s1 / s2;             // likelihood.py:112
     const bool ok = (a.kind == CHB_PGW_FULL) ? !(neff < a.pe_neff) : (neff >= a.pe_neff);
@@ -349,6 +424,23 @@ numerator_f32_kernel(const NumArgs a) {
         for (int i = tid; i < G; i += F_NT) eg[i] = (i == G - 1) ? ub : __dadd_rn(__dmul_rn((double)i, step), lb);
       } else {
         for (int i = tid; i < G; i += F_NT) eg[i] = zgrid[i];
+      }
+    }
+    if (KG == 0 && tid == 0) {
+      // bandwidth (utils/math.py:62-70) and the tiling of the windowed KDE, once per unit
+      sh_win = 0;
+      if (!a.binning) {
+        const double neff_k0 = 1.0 / (s2 / (s1 * s1));
+        double bw0;
+        if (a.bw_method == CHB_BW_SCOTT) bw0 = pow(neff_k0, -0.2) * zstd;
+        else if (a.bw_method == CHB_BW_SILVERMAN) bw0 = pow(neff_k0 * 3.0 / 4.0, -0.2) * zstd;
+        else bw0 = a.bw_value * zstd;
+        sh_bw = bw0;
+        if (a.kernel == CHB_KERNEL_GAUSS && ustep > 0.0 && a.kde_win_iters > 0 && G >= 2) {
+          const double s0 = 0.8493218002880191 / bw0;
+          WinPlan wp;
+          if (win_plan(G, Ns, (float)(ustep * (double)(float)s0), a.kde_win_iters, 32, wp)) { sh_wp = wp; sh_win = 1; }
+        }
       }
     }
     __syncthreads();
@@ -389,28 +481,56 @@ numerator_f32_kernel(const NumArgs a) {
         dxw = xwb; dn = B;
         __syncthreads();
       }
-      const double neff_k = 1.0 / (Q / (W * W));
       double bw;
-      if (a.bw_method == CHB_BW_SCOTT) bw = pow(neff_k, -0.2) * dstd;
-      else if (a.bw_method == CHB_BW_SILVERMAN) bw = pow(neff_k * 3.0 / 4.0, -0.2) * dstd;
-      else bw = a.bw_value * dstd;
-      bool windowed = false;
-      if (a.kernel == CHB_KERNEL_GAUSS && ustep > 0.0 && a.kde_win_iters > 0 && !a.binning && G >= 2) {
-        // windowed recurrence over the sorted samples (kde_win.cuh); chunk tables live in pgw | dens
-        const double s = 0.8493218002880191 / bw;
-        WinPlan wp;
-        const int maxc = (2 * Nz * (int)sizeof(double)) / (int)(sizeof(float4) + sizeof(int2));
-        if (win_plan(G, dn, (float)(ustep * (double)(float)s), a.kde_win_iters, maxc, wp)) {
-          float4* summ = reinterpret_cast<float4*>(pgw);
-          int2* win = reinterpret_cast<int2*>(summ + maxc);
-          kde1d_f32_win<F_NW>(dxw, dn, G, eg[0], ustep, 0.5 * (eg[0] + eg[G - 1]), s, W, wp,
-                              norm * 0.3989422804014327 / bw, summ, win, crs, reinterpret_cast<double*>(part), dens);
-          windowed = true;
-        }
+      if (!a.binning) bw = sh_bw;
+      else {
+        const double neff_k = 1.0 / (Q / (W * W));
+        if (a.bw_method == CHB_BW_SCOTT) bw = pow(neff_k, -0.2) * dstd;
+        else if (a.bw_method == CHB_BW_SILVERMAN) bw = pow(neff_k * 3.0 / 4.0, -0.2) * dstd;
+        else bw = a.bw_value * dstd;
       }
-      if (!windowed) kde_inplace(dxw, dn, eg, G, bw, W, a.kernel, norm, part, F_NW * Nz, dens, ustep);
+      const bool windowed = sh_win != 0;
+      if (windowed) {
+        // windowed recurrence over the sorted samples (kde_win.cuh); chunk tables live in pgw
+        const WinPlan wp = sh_wp;
+        float4* summ = reinterpret_cast<float4*>(pgw);
+        int2* win = reinterpret_cast<int2*>(summ + 32);
+        kde1d_f32_win<F_NW>(dxw, dn, G, eg[0], ustep, 0.5 * (eg[0] + eg[G - 1]), 0.8493218002880191 / bw, W, wp,
+                            norm * 0.3989422804014327 / bw, summ, win, crs, reinterpret_cast<double*>(part), dens);
+      } else {
+        kde_inplace(dxw, dn, eg, G, bw, W, a.kernel, norm, part, F_NW * Nz, dens, ustep);
+      }
       __syncthreads();
-      for (int k = tid; k < Nz; k += F_NT) pgw[k] = interp_lr(zgrid[k], eg, dens, G, 0.0, 0.0);
+      // p_gw on the event grid (likelihood.py:139-141).  When nothing else needs the array, the interpolated value
+      // goes straight into the integrand (same k): no staging, no extra barrier.
+      const bool fused_tail = !pout && (a.kind == CHB_PGW_1D || a.catA != nullptr);
+      const double inv_ustep = (ustep > 0.0) ? 1.0 / ustep : 0.0;
+      auto pgw_at = [&](int k) -> double {
+        const double x = zgrid[k];
+        if (ustep > 0.0) {                        // uniform effective grid: index directly, then settle on the knots
+          if (x < eg[0] || x > eg[G - 1]) return 0.0;
+          int i = (int)((x - eg[0]) * inv_ustep);
+          i = max(0, min(i, G - 2));
+          while (i < G - 2 && x >= eg[i + 1]) ++i;
+          while (i > 0 && x < eg[i]) --i;
+          const double x0 = eg[i], dx = eg[i + 1] - x0, f0 = dens[i], df = dens[i + 1] - f0;
+          return (fabs(dx) <= 4.930380657631324e-32) ? f0 : f0 + ((x - x0) / dx) * df;
+        }
+        return interp_lr(x, eg, dens, G, 0.0, 0.0);
+      };
+      if (fused_tail) {
+        if (a.kind == CHB_PGW_1D) {
+          for (int k = tid; k < Nz; k += F_NT) like_acc += pgw_at(k) * dV[k] * ck[k];
+        } else {
+          const double* A = a.catA + (size_t)ev * Nz;
+          const double* Bk = a.catB + (size_t)ev * Nz;
+          for (int k = tid; k < Nz; k += F_NT) {
+            const double pgs = has_cat ? fR * A[k] + (1.0 - pcompl_ev[k]) * dV[k] * Bk[k] : dV[k] * Bk[k];
+            like_acc += pgw_at(k) * pgs * ck[k];
+          }
+        }
+      } else {
+      for (int k = tid; k < Nz; k += F_NT) pgw[k] = pgw_at(k);
       __syncthreads();
       if (a.kind == CHB_PGW_1D) {
         for (int k = tid; k < Nz; k += F_NT) {
@@ -436,6 +556,7 @@ numerator_f32_kernel(const NumArgs a) {
             like_acc += (pgw[k] * gwp[p]) * pgal * ck[k];
           }
         }
+      }
       }
     } else if (KG == 1) {
       // ---- p_gw3dmarg: per pixel, always Epanechnikov (likelihood.py:160-205) -----------------
@@ -613,37 +734,50 @@ numerator_f32_kernel(const NumArgs a) {
     }
 
     FPHASE(4);
-    const double like = block_sum(like_acc, red);
-    if (tid == 0) { a.log_like[(size_t)h * a.Nev + ev] = nan_to_num_log_f(like); a.like_raw[(size_t)h * a.Nev + ev] = like; }
+    {
+      // one barrier: warp sums -> thread 0 (`red` is idle here; the barrier at the top of the next unit protects it)
+      const double ws = warp_sum(like_acc);
+      if (lane == 0) red[warp] = ws;
+      __syncthreads();
+      if (tid == 0) {
+        double like = 0.0;
+#pragma unroll
+        for (int w = 0; w < F_NW; ++w) like += red[w];
+        a.log_like[(size_t)h * a.Nev + ev] = nan_to_num_log_f(like); a.like_raw[(size_t)h * a.Nev + ev] = like;
+      }
+    }
     FPHASE(5);
   }
   if (a.prof && tid == 0) for (int i = 0; i < 8; ++i) a.prof[(size_t)blockIdx.x * 8 + i] = pacc[i];
 }
 
 static inline int kind_group(int kind) { return kind == CHB_PGW_MARG ? 1 : (kind == CHB_PGW_FULL ? 2 : 0); }
-cudaError_t numerator_f32_configure(int kind, size_t smem) {
-  switch (kind_group(kind)) {
-    case 0: return cudaFuncSetAttribute(numerator_f32_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    case 1: return cudaFuncSetAttribute(numerator_f32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    default: return cudaFuncSetAttribute(numerator_f32_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+// dispatch over (kind group, mode) -> kernel instantiation
+#define CHB_F32_DISPATCH(KG_, MODE_, EXPR)                                                     \
+  switch ((KG_) * 3 + (MODE_)) {                                                               \
+    case 0: { auto kern = numerator_f32_kernel<0, 0>; EXPR; } break;                           \
+    case 1: { auto kern = numerator_f32_kernel<0, 1>; EXPR; } break;                           \
+    case 2: { auto kern = numerator_f32_kernel<0, 2>; EXPR; } break;                           \
+    case 3: { auto kern = numerator_f32_kernel<1, 0>; EXPR; } break;                           \
+    case 4: { auto kern = numerator_f32_kernel<1, 1>; EXPR; } break;                           \
+    case 5: { auto kern = numerator_f32_kernel<1, 2>; EXPR; } break;                           \
+    case 6: { auto kern = numerator_f32_kernel<2, 0>; EXPR; } break;                           \
+    case 7: { auto kern = numerator_f32_kernel<2, 1>; EXPR; } break;                           \
+    default: { auto kern = numerator_f32_kernel<2, 2>; EXPR; } break;                          \
   }
+cudaError_t numerator_f32_configure(int kind, int mode, size_t smem) {
+  cudaError_t e = cudaSuccess;
+  CHB_F32_DISPATCH(kind_group(kind), mode, e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  return e;
 }
-int numerator_f32_ctas_per_sm(int kind, size_t smem) {
+int numerator_f32_ctas_per_sm(int kind, int mode, size_t smem) {
   int n = 0;
-  cudaError_t e;
-  switch (kind_group(kind)) {
-    case 0: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, numerator_f32_kernel<0>, F_NT, smem); break;
-    case 1: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, numerator_f32_kernel<1>, F_NT, smem); break;
-    default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, numerator_f32_kernel<2>, F_NT, smem); break;
-  }
+  cudaError_t e = cudaSuccess;
+  CHB_F32_DISPATCH(kind_group(kind), mode, e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, F_NT, smem));
   if (e != cudaSuccess) { cudaGetLastError(); return 0; }
   return n;
 }
-cudaError_t launch_numerator_f32(const NumArgs& a, int grid, size_t smem, cudaStream_t s) {
-  switch (kind_group(a.kind)) {
-    case 0: numerator_f32_kernel<0><<<grid, F_NT, smem, s>>>(a); break;
-    case 1: numerator_f32_kernel<1><<<grid, F_NT, smem, s>>>(a); break;
-    default: numerator_f32_kernel<2><<<grid, F_NT, smem, s>>>(a); break;
-  }
+cudaError_t launch_numerator_f32(const NumArgs& a, int mode, int grid, size_t smem, cudaStream_t s) {
+  CHB_F32_DISPATCH(kind_group(a.kind), mode, (kern<<<grid, F_NT, smem, s>>>(a)));
   return cudaGetLastError();
 }

@@ -14,4 +14,6 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:nume
   python scripts/profile_run.py 296 4 fp32 > gpurun_out/ncu_numf32_$TAG.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:selection_f32 -s 1 -c 1 -f -o gpurun_out/self32_$TAG \
   python scripts/profile_run.py 148 4 fp32 > gpurun_out/ncu_self32_$TAG.log 2>&1
+timeout 600 ncu --set full --clock-control none -k regex:numerator_f32 -s 3 -c 1 -f -o gpurun_out/numf32_bench_$TAG \
+  python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_numf32_bench_$TAG.log 2>&1
 timeout 300 python scripts/profile_run.py 296 4 fp32 2>&1 | tail -3 | tee gpurun_out/phase_$TAG.log

@@ -35,6 +35,13 @@ for f in os.listdir(tmp):
       line_of[int(m.group(1), 16)] = (cur[0], cur[1], cur_main, m.group(2).strip())
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
+# several kernels in one report: keep the block whose "Kernel Name" row matches NCU_KERNEL_INDEX (default 0)
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+if starts:
+  ki = int(os.environ.get("NCU_KERNEL_INDEX", "0"))
+  lo = starts[ki]
+  hi_ = starts[ki + 1] if ki + 1 < len(starts) else len(rows)
+  rows = rows[lo:hi_]
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[hi]
 ia, isamp, iex = hdr.index("Address"), hdr.index("# Samples"), hdr.index("Instructions Executed")

@@ -162,3 +162,25 @@ def test_synthetic_workload_shapes():
   assert all(v.shape == (1000,) for v in inj.values()) and N >= 1000 and np.all(inj["p_draw"] > 0)
   zg = synth.make_z_grids(ev["dL"], 30)
   assert zg.shape == (5, 30) and np.all(np.diff(zg, axis=1) > 0)
+
+
+def test_sampler_front_end_host_logic():
+  """generate_dict (emcee_utils.py:54-64) and the vectorised log-probability wrapper: walkers outside the
+  prior are never sent to the likelihood, the rest go in ONE batched call."""
+  from chimera_b200 import sampling
+  pos = np.array([[70., 0.3], [10., 0.3], [65., 0.25], [80., 0.9]])
+  d = sampling.generate_dict(pos, ["H0", "Om0"])
+  np.testing.assert_array_equal(d["H0"], pos[:, 0])
+  d = sampling.generate_dict(pos, ["H0", "Om0"], to_calc=np.array([0, 2]))
+  np.testing.assert_array_equal(d["Om0"], [0.3, 0.25])
+  assert sampling.generate_dict(pos[0], ["H0", "Om0"]) == {"H0": 70., "Om0": 0.3}
+  calls = []
+
+  def fake_like(**kw):
+    calls.append({k: np.array(v) for k, v in kw.items()})
+    return -0.5 * ((np.asarray(kw["H0"]) - 70.) / 5.) ** 2
+  lp = sampling.log_prob_fn(fake_like, ["H0", "Om0"], sampling.uniform_log_prior([[20., 140.], [0.05, 0.6]]))
+  out = lp(pos)
+  assert len(calls) == 1 and calls[0]["H0"].tolist() == [70., 65.]
+  np.testing.assert_allclose(out, [0., -np.inf, -0.5, -np.inf])
+  assert lp(pos[1]) == -np.inf and lp(pos[2]) == -0.5
