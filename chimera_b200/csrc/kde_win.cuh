@@ -30,6 +30,9 @@
 
 #define CHB_WIN_T2 30.0f          // terms below 2^-30 of the largest term at a grid point are dropped
 #define CHB_WIN_MAXR 16
+#ifndef CHB_WIN_SPAN
+#define CHB_WIN_SPAN 5          // grid points allowed for the spread of a chunk when the tiling is chosen
+#endif
 
 __device__ __forceinline__ float warp_min_f32(float v) {
   float r; asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v)); return r;
@@ -45,7 +48,7 @@ struct WinPlan { int R, LPS, chunk, nchunks; };
 // Returns false when windows cannot pay (window ~ whole grid, too few samples, grid too coarse).
 __device__ __forceinline__ bool win_plan(int G, int n, float h, int iters, int max_chunks, WinPlan& pl) {
   if (!(h > 0.f) || h > 1.8f || iters <= 0) return false;
-  const int wn = 2 * (int)ceilf(6.2f / h) + 5;
+  const int wn = 2 * (int)ceilf(6.2f / h) + CHB_WIN_SPAN;
   if (10 * wn > 7 * G) return false;
   float best = 1e30f;
   pl.R = 0; pl.LPS = 0;

@@ -310,9 +310,9 @@ numerator_f32_kernel(const NumArgs a) {
         // software pipeline: the packed samples of the NEXT chunk are requested before the current chunk is
         // evaluated, so the L2 latency of the loads overlaps ~350 instructions of arithmetic
         float4 sv[U], nsv[U]; float2 lv[U], nlv[U];
-        int cbase = 0;
-        if (lane == 0) cbase = atomicAdd(&next_chunk, U * 32);     // warps pull U*32-sample chunks
-        cbase = __shfl_sync(0xffffffffu, cbase, 0);
+        // static round-robin of U*32-sample chunks over the warps: every thread sees the same samples on every
+        // run, so the fp32 partial statistics (and with them every per-event value) are bit-reproducible
+        int cbase = warp * (U * 32);
         if (cbase < Ns) {
 #pragma unroll
           for (int u = 0; u < U; ++u) {
@@ -322,9 +322,7 @@ numerator_f32_kernel(const NumArgs a) {
           }
         }
         while (cbase < Ns) {
-          int nbase = 0;
-          if (lane == 0) nbase = atomicAdd(&next_chunk, U * 32);
-          nbase = __shfl_sync(0xffffffffu, nbase, 0);
+          const int nbase = cbase + F_NW * (U * 32);
           if (nbase < Ns) {
 #pragma unroll
             for (int u = 0; u < U; ++u) {
