@@ -55,78 +55,8 @@ __device__ __forceinline__ void kde1d_f32_pass(const float2* __restrict__ xw, in
 // Gaussian pair sums on a UNIFORM grid by recurrence.  Each lane owns R CONSECUTIVE grid points
 // g0, g0+h, ..., g0+(R-1)h (scaled units).  With d = g0 - x':
 //     E_0 = 2^-(d^2),   E_{r+1} = E_r q_r,   q_0 = 2^-(2 h d + h^2),   q_{r+1} = q_r c,   c = 2^-(2 h^2)
-// which is the identity 2^-((d+(r+1)h)^2) = 2^-((d+rh)^2) 2^-(2h(d+rh)+h^2).  Two MUFU.EX2 per R pairs
-// instead of R; the loop becomes FP32-issue-bound (3 FP32 ops per pair).  The run is short (R <= 8) so
-// rounding grows by at most R ulp; the caller guarantees h <= 1 so that a start value flushed to zero
-// (|d| > 11.2) implies every point of the run is below 2^-50 of a unit-height kernel.  The exponent of q
-// is clamped so that 0 * q can never be 0 * inf.
-template <int R, int NW>
-__device__ __forceinline__ void kde1d_f32_rec_pass(const float2* __restrict__ xw, int n, const double* __restrict__ eg,
-                                                   int G, int g_base, double c, double s, float h, float cq,
-                                                   float* __restrict__ part /* [NW][G] */) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int g0 = g_base + lane * R;
-  const float gp = (g0 < G) ? (float)((eg[g0] - c) * s) : 3.0e18f;
-  const float m2h = -2.f * h, mh2 = -h * h;
-  float acc[R];
-#pragma unroll
-  for (int r = 0; r < R; ++r) acc[r] = 0.f;
-  const int per = (n + NW - 1) / NW;
-  const int j0 = min(n, warp * per), j1 = min(n, j0 + per);
-#pragma unroll 4
-  for (int j = j0; j < j1; ++j) {
-    const float2 v = xw[j];
-    const float d = gp - v.x;
-    float e = ex2_ftz(-(d * d));
-    float q = ex2_ftz(fminf(fmaf(d, m2h, mh2), 120.f));
-    acc[0] = fmaf(v.y, e, acc[0]);
-#pragma unroll
-    for (int r = 1; r < R; ++r) {
-      e *= q;
-      if (r + 1 < R) q *= cq;
-      acc[r] = fmaf(v.y, e, acc[r]);
-    }
-  }
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const int g = g0 + r;
-    if (g < G) part[warp * G + g] = acc[r];
-  }
-}
-
-// dens[g] = scale * sum_j w'_j 2^-(g'-x'_j)^2 on a uniform grid (spacing `step` in data units).
-template <int NW>
-__device__ __forceinline__ void kde1d_f32_rec(const float2* __restrict__ xw, int n, const double* __restrict__ eg, int G,
-                                              double c, double s, double step, double scale, float* __restrict__ part,
-                                              double* __restrict__ dens) {
-  int R = 1, best = 1 << 30;
-  for (int r = 8; r >= 2; --r) {
-    int cost = ((G + 32 * r - 1) / (32 * r)) * r;
-    if (cost < best) { best = cost; R = r; }
-  }
-  const float h = (float)(step * s);
-  const float cq = exp2f(-2.f * h * h);
-  for (int gb = 0; gb < G; gb += 32 * R) {
-    switch (R) {
-      case 2: kde1d_f32_rec_pass<2, NW>(xw, n, eg, G, gb, c, s, h, cq, part); break;
-      case 3: kde1d_f32_rec_pass<3, NW>(xw, n, eg, G, gb, c, s, h, cq, part); break;
-      case 4: kde1d_f32_rec_pass<4, NW>(xw, n, eg, G, gb, c, s, h, cq, part); break;
-      case 5: kde1d_f32_rec_pass<5, NW>(xw, n, eg, G, gb, c, s, h, cq, part); break;
-      case 6: kde1d_f32_rec_pass<6, NW>(xw, n, eg, G, gb, c, s, h, cq, part); break;
-      case 7: kde1d_f32_rec_pass<7, NW>(xw, n, eg, G, gb, c, s, h, cq, part); break;
-      default: kde1d_f32_rec_pass<8, NW>(xw, n, eg, G, gb, c, s, h, cq, part); break;
-    }
-  }
-  __syncthreads();
-  for (int g = threadIdx.x; g < G; g += NW * 32) {
-    double acc = 0.0;
-#pragma unroll
-    for (int w = 0; w < NW; ++w) acc += (double)part[w * G + g];
-    dens[g] = acc * scale;
-  }
-}
-
-// Second form of the recurrence with fewer instructions per pair (2 instead of 3):
+// which is the identity 2^-((d+(r+1)h)^2) = 2^-((d+rh)^2) 2^-(2h(d+rh)+h^2).
+// Form used here, with 2 FP32 instructions per pair:
 //     w E_r = [w E_0] q_0^r c^{r(r-1)/2}
 // The constant c^{r(r-1)/2} = 2^-(h^2 r (r-1)) does not depend on the sample, so it is applied ONCE to the
 // accumulator after the loop; inside the loop only p_r = p_{r-1} q_0 (FMUL) and acc_r += [w E_0] p_r (FFMA)

@@ -43,23 +43,27 @@ __device__ __forceinline__ float warp_max_f32(float v) {
 
 struct WinPlan { int R, LPS, chunk, nchunks; };
 
-// Tiling: among R in {4,8,12,16} (run-length bound (R-1) h <= 5.5) and LPS in {2,4,8} the pair with the fewest
-// instructions per sample for the typical window of 2 sqrt(T2 + 8)/h + 1 points (+ the spread of a chunk).
-// Returns false when windows cannot pay (window ~ whole grid, too few samples, grid too coarse).
+// Tiling: the narrowest tile LPS x R (R in {4,8,12,16} grid points per lane under the run-length bound
+// (R-1) h <= 5.5, LPS in {2,4,8} lanes per sample) that covers the typical window of 2 sqrt(T2 + 8)/h + 1 points
+// (+ the spread of a chunk) in ONE pass; the widest admissible tile when none does.  Evaluated by one thread per
+// unit, so it is a short table walk.  Returns false when windows cannot pay (window ~ whole grid, too few samples,
+// grid too coarse for the recurrence).
 __device__ __forceinline__ bool win_plan(int G, int n, float h, int iters, int max_chunks, WinPlan& pl) {
   if (!(h > 0.f) || h > 1.8f || iters <= 0) return false;
   const int wn = 2 * (int)ceilf(6.2f / h) + CHB_WIN_SPAN;
   if (10 * wn > 7 * G) return false;
-  float best = 1e30f;
+  const int rmax = min(CHB_WIN_MAXR, 1 + (int)(5.5f / h));             // (R-1) h <= 5.5
+  // tiles by increasing width; at equal width the longer run (fewer MUFU per pair) comes first
+  const unsigned char tr[12] = {4, 8, 4, 12, 16, 8, 4, 12, 16, 8, 12, 16};
+  const unsigned char tl[12] = {2, 2, 4, 2, 2, 4, 8, 4, 4, 8, 8, 8};
   pl.R = 0; pl.LPS = 0;
-  for (int l = 2, lg = 4; l <= 8; l <<= 1, --lg) {                     // lg = log2(32 / l)
-    for (int r = 4; r <= CHB_WIN_MAXR; r += 4) {
-      if ((float)(r - 1) * h > 5.5f) continue;
-      const int passes = (wn + l * r - 1) / (l * r);
-      const float per_lane = (float)(10 + r + r / 4) + (float)(2 * r * lg + 6 * r + 40) / (float)iters;
-      const float cost = (float)passes * per_lane * (float)l;
-      if (cost < best) { best = cost; pl.R = r; pl.LPS = l; }
-    }
+#pragma unroll
+  for (int i = 0; i < 12; ++i) {
+    const int r = tr[i], l = tl[i];
+    if (r > rmax) continue;
+    if (pl.R == 0 || pl.R * pl.LPS < wn) {                              // still too narrow: take the wider tile
+      if (pl.R == 0 || r * l > pl.R * pl.LPS || (r * l == pl.R * pl.LPS && r > pl.R)) { pl.R = r; pl.LPS = l; }
+    } else if (r * l == pl.R * pl.LPS && r > pl.R) { pl.R = r; pl.LPS = l; }
   }
   if (pl.R == 0) return false;
   // at most 32 chunks (phase B keeps one chunk per lane), each a multiple of 4 sub-stream rounds

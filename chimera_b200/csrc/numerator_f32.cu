@@ -202,7 +202,6 @@ numerator_f32_kernel(const NumArgs a) {
   __shared__ double P[CHB_NPAR];
   __shared__ double HC[CHB_NHC];
   __shared__ double L[8];
-  __shared__ int next_chunk;
   __shared__ float crs[20];
   __shared__ double sh_bw;
   __shared__ WinPlan sh_wp;
@@ -257,7 +256,6 @@ numerator_f32_kernel(const NumArgs a) {
     }
     if (tid < CHB_NPAR) P[tid] = a.hyper[(size_t)h * CHB_NPAR + tid];
     if (tid >= 64 && tid < 64 + CHB_NHC) HC[tid - 64] = a.HC[(size_t)h * CHB_NHC + tid - 64];
-    if (tid == 128) next_chunk = 0;
     if (MODE != 1) {
       const double* zgr = a.zgrids + (size_t)ev * Nz;
       for (int k = tid; k < Nz; k += F_NT) zgrid[k] = zgr[k];
@@ -428,10 +426,11 @@ numerator_f32_kernel(const NumArgs a) {
       // bandwidth (utils/math.py:62-70) and the tiling of the windowed KDE, once per unit
       sh_win = 0;
       if (!a.binning) {
+        // neff^(-1/5) on the MUFU pipe (2e-7 relative): the other 255 threads wait on this value
         const double neff_k0 = 1.0 / (s2 / (s1 * s1));
         double bw0;
-        if (a.bw_method == CHB_BW_SCOTT) bw0 = pow(neff_k0, -0.2) * zstd;
-        else if (a.bw_method == CHB_BW_SILVERMAN) bw0 = pow(neff_k0 * 3.0 / 4.0, -0.2) * zstd;
+        if (a.bw_method == CHB_BW_SCOTT) bw0 = (double)ex2f_(-0.2f * lg2f_((float)neff_k0)) * zstd;
+        else if (a.bw_method == CHB_BW_SILVERMAN) bw0 = (double)ex2f_(-0.2f * lg2f_((float)(neff_k0 * 3.0 / 4.0))) * zstd;
         else bw0 = a.bw_value * zstd;
         sh_bw = bw0;
         if (a.kernel == CHB_KERNEL_GAUSS && ustep > 0.0 && a.kde_win_iters > 0 && G >= 2) {

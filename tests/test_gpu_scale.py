@@ -172,9 +172,12 @@ def test_c5_modified_gravity_walker_batch(cb):
   out = lp(walkers)
   # walkers may legitimately hit the N_eff gate (+inf) or a zero-likelihood event (-inf), exactly like the reference
   assert out.shape == (4096,) and np.all(np.isneginf(out[::500])) and np.mean(np.isfinite(out)) > 0.9
-  # batch independence: the same walkers in chunks of 1000
+  # batch independence: the same walkers in chunks of 1000 (per-event values are bit-identical, test_c3_invariances;
+  # the injection sums are tiled by batch size, so the totals agree to fp64 rounding)
   chunks = np.concatenate([lp(walkers[i:i + 1000]) for i in range(0, 4096, 1000)])
-  np.testing.assert_array_equal(chunks, out)
+  fin = np.isfinite(out)
+  np.testing.assert_array_equal(chunks[~fin], out[~fin])
+  np.testing.assert_allclose(chunks[fin], out[fin], rtol=1e-12)
   # oracle on a few walkers
   pop0 = orc.make_pop(orc.make_cosmo("mg_flrw", z_max=5.), orc.make_mass("plp"), orc.make_rate("madau_dickinson"))
   opts = orc.make_opts(None, "gauss", None, 2.0, False, 200, 2.0)
