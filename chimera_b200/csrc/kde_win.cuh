@@ -41,6 +41,15 @@ __device__ __forceinline__ float warp_max_f32(float v) {
   float r; asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v)); return r;
 }
 
+// Blackwell packed-FP32 arithmetic (PTX f32x2 -> SASS FADD2 / FMUL2 / FFMA2): two samples ride in the two halves of a
+// 64-bit register pair, so the recurrence of the pair sums issues one instruction for two samples.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
 struct WinPlan { int R, LPS, chunk, nchunks; };
 
 // Tiling: the narrowest tile LPS x R (R in {4,8,12,16} grid points per lane under the run-length bound
@@ -122,26 +131,38 @@ __device__ __forceinline__ void kde_win_pass(const float2* __restrict__ xl, int 
   const float top = sm4.z - dr * dr;                     // largest exponent any term of this run can have
   const float Kf = (top > -64.f) ? 0.f : fminf(floorf(100.f - top), 1900.f);
   const float m2h = -2.f * hs, mh2 = -h * h;
-  float acc[R];
+  // Samples are stored in pairs {x'_a, x'_b, lw_a, lw_b} (phase A): one LDS.128 brings two samples as two packed
+  // operands, and the whole recurrence runs on FADD2 / FMUL2 / FFMA2 -- one issue slot for two samples.
+  const float4* __restrict__ xp = reinterpret_cast<const float4*>(xl);
+  const f32x2 gpn2 = pk2(-gp, -gp), mone2 = pk2(-1.f, -1.f), Kp2 = pk2(Kf, Kf);
+  const f32x2 p2h2 = pk2(-m2h, -m2h), mh22 = pk2(mh2, mh2);
+  f32x2 acc2[R];
 #pragma unroll
-  for (int r = 0; r < R; ++r) acc[r] = 0.f;
-#pragma unroll 4
-  for (int j = cb + sub; j < ce; j += S) {
-    const float2 v = xl[j];
-    const float d = gp - v.x;
-    const float e0 = ex2_ftz(fmaf(-d, d, v.y) + Kf);                   // w' 2^(K - d^2)
-    const float q = ex2_ftz(fminf(fmaf(d, m2h, mh2), 31.f));
-    const float q2 = q * q, q3 = q2 * q, q4 = q2 * q2;
-    float p = e0;
+  for (int r = 0; r < R; ++r) acc2[r] = 0ull;
+#pragma unroll 2
+  for (int jp = (cb >> 1) + sub; jp < (ce >> 1); jp += S) {
+    const float4 v = xp[jp];
+    const f32x2 nd = add2(pk2(v.x, v.y), gpn2);                        // x' - g = -d, both samples
+    const f32x2 arg = add2(fma2(mul2(nd, nd), mone2, pk2(v.z, v.w)), Kp2);  // lw - d^2 + K
+    const f32x2 qa = fma2(nd, p2h2, mh22);                             // -(2 hs d + h^2)
+    float a0, a1, b0, b1;
+    upk2(arg, a0, a1); upk2(qa, b0, b1);
+    const f32x2 e0 = pk2(ex2_ftz(a0), ex2_ftz(a1));
+    const f32x2 q = pk2(ex2_ftz(fminf(b0, 31.f)), ex2_ftz(fminf(b1, 31.f)));
+    const f32x2 q2 = mul2(q, q), q3 = mul2(q2, q), q4 = mul2(q2, q2);
+    f32x2 p = e0;
 #pragma unroll
     for (int b = 0; b < R; b += 4) {
-      if (b) p *= q4;
-      acc[b] += p;
-      acc[b + 1] = fmaf(p, q, acc[b + 1]);
-      acc[b + 2] = fmaf(p, q2, acc[b + 2]);
-      acc[b + 3] = fmaf(p, q3, acc[b + 3]);
+      if (b) p = mul2(p, q4);
+      acc2[b] = add2(acc2[b], p);
+      acc2[b + 1] = fma2(p, q, acc2[b + 1]);
+      acc2[b + 2] = fma2(p, q2, acc2[b + 2]);
+      acc2[b + 3] = fma2(p, q3, acc2[b + 3]);
     }
   }
+  float acc[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) { float lo_, hi_; upk2(acc2[r], lo_, hi_); acc[r] = lo_ + hi_; }
   int rbase = 0;
   bool owner = true;
   rs_reduce<R, LPS, R>(acc, lane, rbase, owner);
@@ -183,7 +204,7 @@ __device__ __forceinline__ void kde_win_chunks(const float2* __restrict__ xl, in
   }
 }
 
-// Whole-CTA call (NW warps).  xw: in {x, w} (x sorted or not), out {x', log2 w'}.  Scratch: summ/win hold
+// Whole-CTA call (NW warps).  xw: in {x, w} (x sorted or not, n EVEN), out pairs {x'_a, x'_b, log2 w'_a, log2 w'_b}.  Scratch: summ/win hold
 // pl.nchunks (<= 32) entries, cr 16 floats, rows NW*G doubles.  dens[g] = scale * sum_j w'_j 2^-(g'_g - x'_j)^2 with
 // g'_g = (lb + g step - c) sf, sf = float(s) shared by samples and grid.
 template <int NW>
@@ -203,15 +224,17 @@ __device__ __forceinline__ void kde1d_f32_win(float2* __restrict__ xw, int n, in
   for (int ck = warp; ck < pl.nchunks; ck += NW) {
     const int cb = ck * pl.chunk, ce = min(n, cb + pl.chunk);
     float lo = INFINITY, hi = -INFINITY, lm = -INFINITY, xm = 0.f;
-    for (int j = cb + lane; j < ce; j += 32) {
-      const float2 v = xw[j];
-      const float x = ((v.x - c_hi) - c_lo) * sf;
-      const bool live = v.y > 0.f;                                     // zero / NaN weights add exactly 0
-      const float lw = live ? lg2f_(v.y) + lg2invW : -INFINITY;
-      xw[j] = make_float2(x, lw);
-      lo = fminf(lo, live ? x : INFINITY);
-      hi = fmaxf(hi, live ? x : -INFINITY);
-      if (lw > lm) { lm = lw; xm = x; }
+    float4* __restrict__ xp = reinterpret_cast<float4*>(xw);
+    for (int jp = (cb >> 1) + lane; jp < (ce >> 1); jp += 32) {        // two samples {z_a, w_a, z_b, w_b} per lane
+      const float4 v = xp[jp];
+      const float xa = ((v.x - c_hi) - c_lo) * sf, xb = ((v.z - c_hi) - c_lo) * sf;
+      const bool la = v.y > 0.f, lb_ = v.w > 0.f;                      // zero / NaN weights add exactly 0
+      const float lwa = la ? lg2f_(v.y) + lg2invW : -INFINITY, lwb = lb_ ? lg2f_(v.w) + lg2invW : -INFINITY;
+      xp[jp] = make_float4(xa, xb, lwa, lwb);                          // pair layout of the packed pass loop
+      lo = fminf(lo, fminf(la ? xa : INFINITY, lb_ ? xb : INFINITY));
+      hi = fmaxf(hi, fmaxf(la ? xa : -INFINITY, lb_ ? xb : -INFINITY));
+      if (lwa > lm) { lm = lwa; xm = xa; }
+      if (lwb > lm) { lm = lwb; xm = xb; }
     }
     lo = warp_min_f32(lo); hi = warp_max_f32(hi);
     const float lmw = warp_max_f32(lm);

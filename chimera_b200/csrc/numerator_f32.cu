@@ -434,7 +434,7 @@ numerator_f32_kernel(const NumArgs a) {
         else bw0 = a.bw_value * zstd;
         sh_bw = bw0;
         // the chunk tables (32 x {float4, int2} = 768 B) live in the pgw | dens arrays: 2 Nz doubles
-        if (a.kernel == CHB_KERNEL_GAUSS && ustep > 0.0 && a.kde_win_iters > 0 && G >= 2 && Nz >= 64) {
+        if (a.kernel == CHB_KERNEL_GAUSS && ustep > 0.0 && a.kde_win_iters > 0 && G >= 2 && Nz >= 64 && (Ns & 1) == 0) {
           const double s0 = 0.8493218002880191 / bw0;
           WinPlan wp;
           if (win_plan(G, Ns, (float)(ustep * (double)(float)s0), a.kde_win_iters, 32, wp)) { sh_wp = wp; sh_win = 1; }
