@@ -284,13 +284,20 @@ numerator_f32_kernel(const NumArgs a) {
         }
       }
     }
+    // MODE 2: the unit statistics written by the reweighting kernel are requested BEFORE waiting for the sample
+    // copy, so their L2 latency hides behind the TMA instead of sitting in front of the next barrier
+    double s1 = 0.0, s2 = 0.0, zmn = 0.0, zmx = 0.0, zstd = 0.0;
+    if (MODE == 2) {
+      const double2* us = reinterpret_cast<const double2*>(a.unit_stats + (size_t)unit * 8);
+      const double2 u0 = __ldg(us), u1 = __ldg(us + 1);
+      s1 = u0.x; s2 = u0.y; zmn = u1.x; zmx = u1.y; zstd = __ldg(a.unit_stats + (size_t)unit * 8 + 4);
+    }
     FPHASE(1);
     mbar_wait(&bar, phase);
     phase ^= 1;
     FPHASE(0);
 
     const size_t so = (size_t)ev * Ns;
-    double s1, s2, zmn, zmx, zstd;
     if (MODE != 2) {
       fc.cd4_last = fc.cd4[fc.rm - 1];
       // ---- stage 1: reweighting (pop_wrapper.py:67-80) ------------------------------------------
@@ -389,9 +396,6 @@ numerator_f32_kernel(const NumArgs a) {
         }
         continue;
       }
-    } else {
-      const double* us = a.unit_stats + (size_t)unit * 8;
-      s1 = us[0]; s2 = us[1]; zmn = us[2]; zmx = us[3]; zstd = us[4];
     }
     const double norm = s1 / Ns;                  // likelihood.py:111
     const double neff = s1 * s1 / s2;             // likelihood.py:112

@@ -70,6 +70,27 @@ def test_no_gpu_fails_loudly(lib):
     cb.cosmo.dL_at_z(cb.cosmo.flrw(), np.array([0.1]))
   out = np.zeros(1)
   assert lib.chb_mufu_peak(0, 0.01, _lib.dptr(out)) == _lib.ERR_CUDA
+  # the setup-side entry points (HEALPix, pixelisation, p_cat) have no host fallback either
+  with pytest.raises(RuntimeError):
+    cb.sky.ang2pix(8, np.array([0.3]), np.array([1.0]))
+  with pytest.raises(RuntimeError):
+    cb.sky.pix2ang(8, np.array([5]))
+  th = cb.theta_pe_det(dL=np.ones((1, 4)), ra=np.full((1, 4), 0.1), dec=np.full((1, 4), 0.2))
+  with pytest.raises(RuntimeError):
+    cb.pixelize_gw_catalog(th, [8], 4, 0.9)
+
+
+def test_setup_entry_points_validate_before_touching_the_device(lib):
+  """nside must be a power of two and angles in range (healpy raises ValueError): checked on the host first."""
+  import chimera_b200 as cb
+  with pytest.raises(ValueError):
+    cb.sky.ang2pix(12, np.array([0.3]), np.array([1.0]))
+  with pytest.raises(ValueError):
+    cb.sky.ang2pix(8, np.array([-0.3]), np.array([1.0]))
+  with pytest.raises(ValueError):
+    cb.sky.pix2ang(8, np.array([12 * 64]))
+  with pytest.raises(NotImplementedError):
+    cb.sky.ang2pix(8, 0.1, 0.1, nest=True)
 
 
 def test_config_validation(lib):
