@@ -241,11 +241,13 @@ numerator_f32_kernel(const NumArgs a) {
   const long long units = (long long)a.Nev * a.n_hyper;
   for (long long unit = blockIdx.x; unit < units; unit += gridDim.x) {
     const int ev = (int)(unit / a.n_hyper), h = (int)(unit % a.n_hyper);
+    // every thread orders its generic-proxy writes to the staging buffers of the previous unit before the barrier;
+    // after it one thread may hand the buffers to the async proxy (TMA bulk copy) again
+    fence_proxy_async();
     __syncthreads();
     const double* tblk = a.tabs + (size_t)h * lay.total() + lay.off_f32();
     float2* zw = (MODE == 1) ? a.zw_stage + (size_t)unit * Ns : zw_s;
     if (tid == 0) {
-      fence_proxy_async();
       if (MODE != 2) {
         mbar_expect_tx(&bar, tab_bytes);
         bulk_g2s(tab, tblk + lay.f32_dl4(), tab_bytes, &bar);
