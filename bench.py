@@ -68,7 +68,7 @@ def build_workload(args, rank):
               z_range=np.array([0.073, 1.3]))
 
 
-def build_likelihood(w, fp_mode, distributed):
+def build_likelihood(w, fp_mode, distributed, kernel="gauss", binning=False):
   import chimera_b200 as cb
   ev = w["ev"]
   th = cb.theta_pe_det(**{k: ev[k] for k in ("m1det", "m2det", "dL", "pe_prior", "ra", "dec", "opt_nsides",
@@ -77,7 +77,7 @@ def build_likelihood(w, fp_mode, distributed):
   gcat = cb.pixelated_catalog(cb.dVdz_completeness(w["z_range"]), p_cat=w["p_cat"], P_compl=w["P_compl"])
   pop = cb.population(cb.cosmo.flrw(H0=70., Om0=0.25, z_max=5.), cb.mass.plp(), cb.rate.madau_dickinson(), gal_cat=gcat)
   sel = cb.selection_function(cb.theta_inj_det(**w["inj"]), w["N_inj"], N_eff=5.)
-  return cb.hyperlikelihood(th, w["zg"], pop, sel, kind_p_gw3d="approximate", kernel="gauss", binning=False,
+  return cb.hyperlikelihood(th, w["zg"], pop, sel, kind_p_gw3d="approximate", kernel=kernel, binning=binning, num_bins=200,
                             cut_grid=2.0, pe_neff=2.0, fp_mode=fp_mode, distributed=distributed, presharded=True)
 
 
@@ -358,8 +358,25 @@ def run_ours(args, rank, world, local_rank):
     "gpu_launches": int(launches), "clocks": clocks,
   }
   if world == 1 and not args.no_cpu_baseline:
+    # the same workload with the reference's DEFAULT KDE options (Epanechnikov kernel, 200 bins),
+    # for comparison only: 3 warm-up + 3 timed device-resident steps
+    del like
+    like_d = build_likelihood(w, args.fp_mode, False, kernel="epan", binning=True)
+    for _ in range(3):
+      like_d.partials_device(d_rows, d_part)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(3):
+      like_d.partials_device(d_rows, d_part)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_d = e0.elapsed_time(e1) / 3
+    line["reference_default_kde"] = {"value": units_global / (ms_d * 1e-3), "unit": UNIT, "ms_per_step": ms_d,
+                                     "config": "same workload, kernel='epan', binning=True, num_bins=200 (reference defaults)"}
+    del like_d
+    like = build_likelihood(w, args.fp_mode, False)
     procs = 1
-    r = cpu_oracle_rate(w, n_events=160, n_hyper=8, procs=procs)
+    r = cpu_oracle_rate(w, n_events=240, n_hyper=8, procs=procs)
     line["cpu_baseline"] = {"value": r["rate"], "unit": UNIT, "cores": procs, "kind": "port",
                             "sample": f"{r['n_events']} events x 8 hyper-points + full {args.ninj} injections x 8 hyper-points "
                                       f"({r['seconds']:.1f} s of CPU work); value = Nev/(Nev*t_unit+t_sel)",
