@@ -369,6 +369,7 @@ static int eval_impl(chb_handle* h, int64_t n_hyper, const double* d_hyper, doub
     a.binning = (c.kind_p_gw == CHB_PGW_FULL) ? 0 : c.binning; a.num_bins = c.num_bins; a.fp_mode = c.fp_mode;
     a.bw_value = c.bw_value; a.cut_grid = c.cut_grid; a.pe_neff = c.pe_neff;
     { const char* e = getenv("CHB_KDE_DIRECT"); a.rec_off = (e && e[0] == '1') ? 1 : 0; }
+    { const char* e = getenv("CHB_BIN_RUNS"); a.bin_runs = (e && e[0] == '0') ? 0 : 1; }
     { const char* e = getenv("CHB_KDE_WIN"); a.kde_win_iters = e ? atoi(e) : 32; if (!h->sorted) a.kde_win_iters = 0; }
     a.Nev = (int)h->Nev; a.Ns = (int)h->Ns; a.Nz = (int)h->Nz; a.P = (int)std::max<int64_t>(h->P, 1);
     a.m1d = h->m1d.p; a.m2d = h->m2d.p; a.dL = h->dL.p; a.prior = h->prior.p; a.ra = h->ra.p; a.dec = h->dec.p;
