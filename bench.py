@@ -358,9 +358,22 @@ def run_ours(args, rank, world, local_rank):
     "gpu_launches": int(launches), "clocks": clocks,
   }
   if world == 1 and not args.no_cpu_baseline:
+    procs = 1
+    r = cpu_oracle_rate(w, n_events=240, n_hyper=8, procs=procs)
+    line["cpu_baseline"] = {"value": r["rate"], "unit": UNIT, "cores": procs, "kind": "port",
+                            "sample": f"{r['n_events']} events x 8 hyper-points + full {args.ninj} injections x 8 hyper-points "
+                                      f"({r['seconds']:.1f} s of CPU work); value = Nev/(Nev*t_unit+t_sel)",
+                            "t_unit_ms": 1e3 * r["t_unit"], "t_sel_s": r["t_sel"]}
+    # cross-check of the timed configuration against the oracle on the sampled units
+    idx = np.linspace(0, n_hyper - 1, 8).astype(int)
+    lle = like.compute_all(**{k: v[idx] for k, v in w["hyper"].items()})[0][:, :r["n_events"]]
+    ref = np.nan_to_num(r["lle"], nan=-np.inf)
+    fin = np.isfinite(ref) & (np.abs(ref) < 1e300)
+    line["parity_check"] = {"max_err_vs_oracle": float(np.max(np.abs(lle[fin] - ref[fin]) / np.maximum(np.abs(ref[fin]), 1.0))),
+                            "metric": "|d log L| / max(|log L|, 1) per (event, hyper-point)", "units": int(fin.sum())}
+    del like
     # the same workload with the reference's DEFAULT KDE options (Epanechnikov kernel, 200 bins),
     # for comparison only: 3 warm-up + 3 timed device-resident steps
-    del like
     try:
       like_d = build_likelihood(w, args.fp_mode, False, kernel="epan", binning=True)
       for _ in range(3):
@@ -377,20 +390,6 @@ def run_ours(args, rank, world, local_rank):
       del like_d
     except Exception as exc:       # a side measurement must never cost the headline line
       line["reference_default_kde"] = {"error": repr(exc)}
-    like = build_likelihood(w, args.fp_mode, False)
-    procs = 1
-    r = cpu_oracle_rate(w, n_events=240, n_hyper=8, procs=procs)
-    line["cpu_baseline"] = {"value": r["rate"], "unit": UNIT, "cores": procs, "kind": "port",
-                            "sample": f"{r['n_events']} events x 8 hyper-points + full {args.ninj} injections x 8 hyper-points "
-                                      f"({r['seconds']:.1f} s of CPU work); value = Nev/(Nev*t_unit+t_sel)",
-                            "t_unit_ms": 1e3 * r["t_unit"], "t_sel_s": r["t_sel"]}
-    # cross-check of the timed configuration against the oracle on the sampled units
-    idx = np.linspace(0, n_hyper - 1, 8).astype(int)
-    lle = like.compute_all(**{k: v[idx] for k, v in w["hyper"].items()})[0][:, :r["n_events"]]
-    ref = np.nan_to_num(r["lle"], nan=-np.inf)
-    fin = np.isfinite(ref) & (np.abs(ref) < 1e300)
-    line["parity_check"] = {"max_err_vs_oracle": float(np.max(np.abs(lle[fin] - ref[fin]) / np.maximum(np.abs(ref[fin]), 1.0))),
-                            "metric": "|d log L| / max(|log L|, 1) per (event, hyper-point)", "units": int(fin.sum())}
   print(json.dumps(line), flush=True)
 
 
