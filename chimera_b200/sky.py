@@ -74,8 +74,20 @@ def _get_threshold(norm_counts, level):
 
 
 def compute_sky_conf_event(healpix_pe, sky_conf, nside):
-  """data.py:246-260: pixels whose sample fraction reaches the `sky_conf` credible level (sparse counts:
-  pixels without samples have p = 0 and can only pass when the threshold itself is 0)."""
+  """data.py:246-260: pixels whose sample fraction reaches the `sky_conf` credible level.  The reference fills a
+  dense map of 12 nside^2 fractions and sorts it; pixels without samples hold 0 and sort last, so the threshold
+  (`_get_threshold`) only ever depends on the occupied pixels: the same index is found on the sparse counts."""
+  unique, counts = np.unique(healpix_pe, return_counts=True)
+  p = counts / healpix_pe.shape[0]
+  prob_sorted = np.sort(p)[::-1]
+  idx = np.searchsorted(np.cumsum(prob_sorted), sky_conf)
+  if idx >= prob_sorted.size:          # the dense map would index a pixel without samples (or run off its end)
+    return _compute_sky_conf_event_dense(healpix_pe, sky_conf, nside)
+  return unique[p >= prob_sorted[idx]]
+
+
+def _compute_sky_conf_event_dense(healpix_pe, sky_conf, nside):
+  """The reference's literal procedure (dense map), kept for the degenerate levels and as the checker."""
   unique, counts = np.unique(healpix_pe, return_counts=True)
   p = np.zeros(nside2npix(nside))
   p[unique] = counts / healpix_pe.shape[0]

@@ -184,3 +184,17 @@ def test_sampler_front_end_host_logic():
   assert len(calls) == 1 and calls[0]["H0"].tolist() == [70., 65.]
   np.testing.assert_allclose(out, [0., -np.inf, -0.5, -np.inf])
   assert lp(pos[1]) == -np.inf and lp(pos[2]) == -0.5
+
+
+def test_sky_conf_sparse_equals_dense():
+  """sky.compute_sky_conf_event (sparse counts) == the reference's dense-map procedure (data.py:246-260)."""
+  from chimera_b200 import sky
+  rng = np.random.default_rng(5)
+  for nside in (8, 64, 256):
+    npix = 12 * nside * nside
+    for _ in range(20):
+      centre = rng.integers(0, npix)
+      pe = np.clip(centre + np.round(rng.normal(0, rng.uniform(0.5, 30), 700)).astype(np.int64), 0, npix - 1)
+      for level in (0.3, 0.5, 0.9, 0.99, 0.999):
+        np.testing.assert_array_equal(sky.compute_sky_conf_event(pe, level, nside),
+                                      sky._compute_sky_conf_event_dense(pe, level, nside))
