@@ -25,6 +25,12 @@
 //    to the samples; when the nearest possible term is below 2^-64 the lane adds an integer exponent offset K
 //    so that the start value cannot flush to zero.  Partial sums go to a per-warp row of doubles (exact
 //    rescaling by 2^-K, no atomics, bit-reproducible).
+//  * What is guaranteed (checked on the CPU by tests/test_window_algorithm.py with a NumPy model of this file, and on
+//    the GPU against the fp64 oracle): absolute error < 2e-6 of the peak everywhere, relative error at fp32 level
+//    wherever the density exceeds 1e-8 of the peak AND at every grid point outside the span of the samples, down to
+//    the fp64 range.  Not guaranteed: relative accuracy inside a gap BETWEEN samples that is wider than ~12 scaled
+//    units (14 bandwidths), where a run that starts > 11.2 units from an isolated sample flushes its start value
+//    (terms below 2^-32 of that sample's weight) -- the same floor the full-grid recurrence of kde_f32.cuh has.
 #pragma once
 #include "kde_f32.cuh"
 
