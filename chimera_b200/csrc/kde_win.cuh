@@ -27,8 +27,9 @@
 //    rescaling by 2^-K, no atomics, bit-reproducible).
 //  * What is guaranteed (checked on the CPU by tests/test_window_algorithm.py with a NumPy model of this file, and on
 //    the GPU against the fp64 oracle): absolute error < 2e-6 of the peak everywhere, relative error at fp32 level
-//    wherever the density exceeds 1e-8 of the peak AND at every grid point outside the span of the samples, down to
-//    the fp64 range.  Not guaranteed: relative accuracy inside a gap BETWEEN samples that is wider than ~12 scaled
+//    wherever the density exceeds 1e-8 of the peak AND at every grid point outside the span of the samples down to
+//    1e-120 of the peak for every tiling (1e-280 on the fine grids of the default bandwidth: a run's far end is
+//    carried in fp32 while 2 h d (R-1) stays below ~200 bits).  Not guaranteed: relative accuracy inside a gap BETWEEN samples that is wider than ~12 scaled
 //    units (14 bandwidths), where a run that starts > 11.2 units from an isolated sample flushes its start value
 //    (terms below 2^-32 of that sample's weight) -- the same floor the full-grid recurrence of kde_f32.cuh has.
 #pragma once

@@ -89,3 +89,35 @@ def test_window_model_deep_tails(seed):
   assert (np.abs(dens[outside] - exact[outside]) / exact[outside]).max() < 2e-4
   core = exact > 1e-8 * exact.max()
   assert (np.abs(dens[core] - exact[core]) / exact[core]).max() < 3e-5
+
+
+@pytest.mark.parametrize("mult", [0.05, 0.08, 0.12, 0.18, 0.25, 0.35, 0.5])
+def test_window_model_all_tilings(mult):
+  """Scalar bandwidths from 0.05 to 0.5 sigma walk through the tilings (R, LPS) = (4,4) (4,8) (8,4) (12,4) (16,4) (12,8)
+  (16,8).  Along a run the terms fall by q = 2^-(2 h d + h^2) per grid point, so fp32 carries a run's far end only
+  while 2 h d (R-1) stays below ~200 bits: the tail guarantee is asserted down to 1e-120 of the peak, which every
+  tiling reaches (the fine grids of the default bandwidth reach 1e-280, test_window_model_deep_tails)."""
+  rng = np.random.default_rng(int(mult * 1000))
+  seen = set()
+  for n in (5000, 2048, 20000):
+    z = np.sort(rng.normal(0.5, 0.05, n))
+    w = rng.random(n) ** 2 * (rng.random(n) > 0.1)
+    bw = mult * z.std()
+    lb, ub = z.min() - 2 * z.std(), z.max() + 2 * z.std()
+    step = (ub - lb) / 149
+    out = kde_window(z, w, lb, step, 150, bw)
+    if out is None:
+      continue
+    dens, info = out
+    seen.add((info["R"], info["LPS"]))
+    lt, exact = _exact(z, w, lb, step, 150, bw)
+    g = lb + step * np.arange(150)
+    live = w > 0
+    assert np.abs(dens - exact).max() < 3e-6 * exact.max()
+    core = exact > 1e-8 * exact.max()
+    assert (np.abs(dens[core] - exact[core]) / exact[core]).max() < 1e-4
+    outside = ((g < z[live].min()) | (g > z[live].max())) & (exact > 1e-120 * exact.max())
+    if outside.any():
+      # (fp32 rounding of d^2 at d ~ 20 scaled units: 2 d ulp(d) ln 2 ~ 1e-4)
+      assert (np.abs(dens[outside] - exact[outside]) / exact[outside]).max() < 5e-4
+  assert seen
