@@ -30,6 +30,9 @@
 #ifndef CHB_K1_U
 #define CHB_K1_U 2           // samples in flight per thread in the reweighting loop (x2 with the prefetch)
 #endif
+#ifndef CHB_K3_MINB
+#define CHB_K3_MINB 6        // co-resident CTAs per SM of the 4-warp KDE variant (MODE 3, experimental)
+#endif
 #ifndef CHB_K2_MINB
 #define CHB_K2_MINB 3        // co-resident CTAs per SM of the KDE/z-integral kernel (MODE 2)
 #endif
@@ -38,7 +41,7 @@ struct FPlan {
   int tab, zgrid, dV, ck, pgw, eg, dens, bc, bs, xwb, part, red, stage, total;
 };
 // mode 0: fused kernel; 1: reweighting only (table + reduction scratch); 2: KDE + z-integral on staged samples (no table)
-__host__ __device__ inline FPlan make_fplan(int tab_doubles, int Nz, int B, int Ns, int kind, int mode = 0) {
+__host__ __device__ inline FPlan make_fplan(int tab_doubles, int Nz, int B, int Ns, int kind, int mode = 0, int nw = F_NW) {
   FPlan p;
   int o = 0;
   p.tab = o; o += (mode == 2) ? 0 : tab_doubles;
@@ -57,7 +60,7 @@ __host__ __device__ inline FPlan make_fplan(int tab_doubles, int Nz, int B, int 
   p.bc = o; o += B;
   p.bs = o; o += B;
   p.xwb = o; o += B;
-  p.part = o; o += (F_NW * Nz + 1) / 2;
+  p.part = o; o += (nw * Nz + 1) / 2;
   p.red = o; o += 64;
   o = (o + 1) & ~1;
   p.stage = o; o += (kind == CHB_PGW_FULL ? 3 : 1) * Ns;     // float2 {z,w} [+ float4 whitened]
@@ -79,7 +82,8 @@ __device__ __forceinline__ double nan_to_num_log_f(double like) {
 
 // sum of 4 doubles + min/max of a float over the CTA in one barrier pair; result in all threads
 struct Stats6 { double a, b, c, d; float mn, mx; };
-__device__ __forceinline__ Stats6 block_stats(Stats6 v, double* red /* >= 6*F_NW doubles */) {
+template <int NW>
+__device__ __forceinline__ Stats6 block_stats(Stats6 v, double* red /* >= 6*NW doubles */) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -98,7 +102,7 @@ __device__ __forceinline__ Stats6 block_stats(Stats6 v, double* red /* >= 6*F_NW
   __syncthreads();
   Stats6 r = {0.0, 0.0, 0.0, 0.0, INFINITY, -INFINITY};
 #pragma unroll
-  for (int i = 0; i < F_NW; ++i) {
+  for (int i = 0; i < NW; ++i) {
     r.a += red[i * 6 + 0]; r.b += red[i * 6 + 1]; r.c += red[i * 6 + 2]; r.d += red[i * 6 + 3];
     r.mn = fminf(r.mn, (float)red[i * 6 + 4]); r.mx = fmaxf(r.mx, (float)red[i * 6 + 5]);
   }
@@ -108,6 +112,7 @@ __device__ __forceinline__ Stats6 block_stats(Stats6 v, double* red /* >= 6*F_NW
 // rescale a float2 {x, w} data set in place to {(x - c) s, w / W} and run the fp32 pair sums
 // `ustep` > 0: eg is a uniform grid with that spacing -> Gaussian sums by recurrence when the scaled
 // spacing allows it (kde_f32.cuh).
+template <int NT>
 __device__ __forceinline__ void kde_inplace(float2* xw, int n, const double* __restrict__ eg, int G, double bw, double W,
                                             int kernel, double scale_pdf, float* part, int part_floats, double* dens,
                                             double ustep = 0.0) {
@@ -117,21 +122,21 @@ __device__ __forceinline__ void kde_inplace(float2* xw, int n, const double* __r
   const double invW = 1.0 / W;
   int R = 0, LPS = 0;
   const float h = (float)(ustep * s);
-  const bool rec = (kernel == CHB_KERNEL_GAUSS) && ustep > 0.0 && G >= 2 && rec2_choose(G, h, part_floats, F_NW, R, LPS);
+  const bool rec = (kernel == CHB_KERNEL_GAUSS) && ustep > 0.0 && G >= 2 && rec2_choose(G, h, part_floats, NT / 32, R, LPS);
   if (rec) {
-    for (int j = threadIdx.x; j < n; j += F_NT) {
+    for (int j = threadIdx.x; j < n; j += NT) {
       const float2 v = xw[j];
       xw[j] = make_float2((float)(((double)v.x - c) * s), lg2f_((float)((double)v.y * invW)));
     }
     __syncthreads();
-    kde1d_f32_rec2<F_NW>(xw, n, eg, G, c, s, h, R, LPS, scale_pdf * knorm / bw, part, dens);
+    kde1d_f32_rec2<NT / 32>(xw, n, eg, G, c, s, h, R, LPS, scale_pdf * knorm / bw, part, dens);
   } else {
-    for (int j = threadIdx.x; j < n; j += F_NT) {
+    for (int j = threadIdx.x; j < n; j += NT) {
       const float2 v = xw[j];
       xw[j] = make_float2((float)(((double)v.x - c) * s), (float)((double)v.y * invW));
     }
     __syncthreads();
-    kde1d_f32<F_NW>(xw, n, eg, G, c, s, kernel, scale_pdf * knorm / bw, part, dens);
+    kde1d_f32<NT / 32>(xw, n, eg, G, c, s, kernel, scale_pdf * knorm / bw, part, dens);
   }
 }
 
@@ -194,9 +199,10 @@ cudaError_t launch_zgrid_terms(const NumArgs& a, int h0, int nh, cudaStream_t s)
 // samples {z, w} and the unit statistics go to the stage buffers in global memory; 2 = KDE + z-integral on the
 // staged samples of a unit (one TMA bulk copy into shared memory).  Splitting lets either half run with three
 // co-resident CTAs per SM (no 42 KB table block next to the 40 KB sample stage) -- see DESIGN.md section 4.
-template <int KG, int MODE>
-__global__ void __launch_bounds__(F_NT, MODE == 0 ? 2 : (MODE == 1 ? CHB_K1_MINB : CHB_K2_MINB))
+template <int KG, int MODE, int NT>
+__global__ void __launch_bounds__(NT, MODE == 0 ? 2 : (MODE == 1 ? CHB_K1_MINB : (MODE == 2 ? CHB_K2_MINB : CHB_K3_MINB)))
 numerator_f32_kernel(const NumArgs a) {
+  constexpr int NW = NT / 32;
   extern __shared__ __align__(16) double sm[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ double P[CHB_NPAR];
@@ -210,7 +216,7 @@ numerator_f32_kernel(const NumArgs a) {
   const TableLayout lay = a.mc.lay;
   const int Ns = a.Ns, Nz = a.Nz, Pp = a.P, B = a.binning ? a.num_bins : 0;
   const int tabd = lay.f32_total() - lay.f32_dl4();
-  const FPlan pl = make_fplan(tabd, Nz, B, Ns, a.kind, MODE);
+  const FPlan pl = make_fplan(tabd, Nz, B, Ns, a.kind, MODE, NW);
   double* tab = sm + pl.tab;
   double* zgrid = sm + pl.zgrid;
   double* dV = sm + pl.dV;
@@ -260,7 +266,7 @@ numerator_f32_kernel(const NumArgs a) {
     if (tid >= 64 && tid < 64 + CHB_NHC) HC[tid - 64] = a.HC[(size_t)h * CHB_NHC + tid - 64];
     if (MODE != 1) {
       const double* zgr = a.zgrids + (size_t)ev * Nz;
-      for (int k = tid; k < Nz; k += F_NT) zgrid[k] = zgr[k];
+      for (int k = tid; k < Nz; k += NT) zgrid[k] = zgr[k];
     }
     __syncthreads();
 
@@ -276,9 +282,9 @@ numerator_f32_kernel(const NumArgs a) {
     if (MODE != 1) {
       if (a.zterms) {
         const float2* zt = a.zterms + ((size_t)(h - a.zterms_h0) * a.Nev + ev) * Nz;
-        for (int k = tid; k < Nz; k += F_NT) { const float2 v = __ldg(zt + k); dV[k] = (double)v.x; ck[k] = (double)v.y; }
+        for (int k = tid; k < Nz; k += NT) { const float2 v = __ldg(zt + k); dV[k] = (double)v.x; ck[k] = (double)v.y; }
       } else {
-        for (int k = tid; k < Nz; k += F_NT) {
+        for (int k = tid; k < Nz; k += NT) {
           const double z = zgrid[k];
           const double zl = (k > 0) ? zgrid[k - 1] : z, zr = (k < Nz - 1) ? zgrid[k + 1] : z;
           const float2 v = zgrid_terms_f32(fc, cr, P, HC, cm, z, 0.5 * (zr - zl));
@@ -329,7 +335,7 @@ numerator_f32_kernel(const NumArgs a) {
           }
         }
         while (cbase < Ns) {
-          const int nbase = cbase + F_NW * (U * 32);
+          const int nbase = cbase + NW * (U * 32);
           if (nbase < Ns) {
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -386,7 +392,7 @@ numerator_f32_kernel(const NumArgs a) {
       }
       FPHASE(2);
       st.a = (double)fa; st.b = (double)fb; st.c = (double)fcs; st.d = (double)fd;
-      st = block_stats(st, red);
+      st = block_stats<NW>(st, red);
       s1 = st.a; s2 = st.b;
       zmn = (double)st.mn; zmx = (double)st.mx;
       const double dzmean = st.c / Ns;
@@ -408,7 +414,7 @@ numerator_f32_kernel(const NumArgs a) {
     const int npix = pixelated ? a.neff_pix[ev] : 1;
 
     if (!ok) {
-      if (pout) for (int i = tid; i < (pixelated ? Pp : 1) * Nz; i += F_NT) pout[i] = 0.0;
+      if (pout) for (int i = tid; i < (pixelated ? Pp : 1) * Nz; i += NT) pout[i] = 0.0;
       if (tid == 0) { a.log_like[(size_t)h * a.Nev + ev] = nan_to_num_log_f(0.0); a.like_raw[(size_t)h * a.Nev + ev] = 0.0; }
       continue;
     }
@@ -423,9 +429,9 @@ numerator_f32_kernel(const NumArgs a) {
         const double ub = zmx + a.cut_grid * zstd;
         const double step = (ub - lb) / (double)(G - 1);
         ustep = a.rec_off ? 0.0 : step;
-        for (int i = tid; i < G; i += F_NT) eg[i] = (i == G - 1) ? ub : __dadd_rn(__dmul_rn((double)i, step), lb);
+        for (int i = tid; i < G; i += NT) eg[i] = (i == G - 1) ? ub : __dadd_rn(__dmul_rn((double)i, step), lb);
       } else {
-        for (int i = tid; i < G; i += F_NT) eg[i] = zgrid[i];
+        for (int i = tid; i < G; i += NT) eg[i] = zgrid[i];
       }
     }
     if (KG == 0 && tid == 0) {
@@ -461,7 +467,7 @@ numerator_f32_kernel(const NumArgs a) {
       double W = s1, Q = s2, dstd = zstd;
       if (a.binning) {                           // utils/math.py:32-46
         const double step = (zmx - zmn) / (double)B;
-        for (int i = tid; i < B; i += F_NT) {
+        for (int i = tid; i < B; i += NT) {
           double e0 = __dadd_rn(__dmul_rn((double)i, step), zmn);
           double e1 = (i + 1 == B) ? zmx : __dadd_rn(__dmul_rn((double)(i + 1), step), zmn);
           bc[i] = (e0 + e1) / 2;
@@ -472,7 +478,7 @@ numerator_f32_kernel(const NumArgs a) {
           // The samples are sorted by dL, hence by z: a bin is a contiguous run of samples.  Every thread walks a
           // contiguous block, sums each run in a register and touches shared memory once per run (2-3 atomics per
           // thread instead of one contended fp64 atomic per sample).  Correct for any order; only fast when sorted.
-          const int per = (Ns + F_NT - 1) / F_NT;
+          const int per = (Ns + NT - 1) / NT;
           const int ja = min(Ns, tid * per), jb = min(Ns, ja + per);
           const double invB = (double)B / (zmx - zmn);
           int cur = -1;
@@ -490,7 +496,7 @@ numerator_f32_kernel(const NumArgs a) {
           }
           if (cur >= 0) atomicAdd(&bs[cur], run);
         } else {
-          for (int j = tid; j < Ns; j += F_NT) {
+          for (int j = tid; j < Ns; j += NT) {
             const float2 v = zw[j];
             double f = floor(((double)v.x - zmn) / (zmx - zmn) * B);
             if (!isnan(f)) atomicAdd(&bs[(int)fmin(fmax(f, 0.0), (double)(B - 1))], (double)v.y);
@@ -498,12 +504,12 @@ numerator_f32_kernel(const NumArgs a) {
         }
         __syncthreads();
         Stats6 t = {0.0, 0.0, 0.0, 0.0, 0.f, 0.f};
-        for (int i = tid; i < B; i += F_NT) { t.a += bs[i]; t.b += bs[i] * bs[i]; t.c += bc[i]; t.d += bc[i] * bc[i]; }
-        t = block_stats(t, red);
+        for (int i = tid; i < B; i += NT) { t.a += bs[i]; t.b += bs[i] * bs[i]; t.c += bc[i]; t.d += bc[i] * bc[i]; }
+        t = block_stats<NW>(t, red);
         W = t.a; Q = t.b;
         const double cmean = t.c / B;
         dstd = sqrt(fmax(t.d / B - cmean * cmean, 0.0));
-        for (int i = tid; i < B; i += F_NT) xwb[i] = make_float2((float)bc[i], (float)bs[i]);
+        for (int i = tid; i < B; i += NT) xwb[i] = make_float2((float)bc[i], (float)bs[i]);
         // (bin centres are O(1) numbers: the float cast before centring costs 6e-8 relative, like z itself)
         dxw = xwb; dn = B;
         __syncthreads();
@@ -522,10 +528,10 @@ numerator_f32_kernel(const NumArgs a) {
         const WinPlan wp = sh_wp;
         float4* summ = reinterpret_cast<float4*>(pgw);
         int2* win = reinterpret_cast<int2*>(summ + 32);
-        kde1d_f32_win<F_NW>(dxw, dn, G, eg[0], ustep, 0.5 * (eg[0] + eg[G - 1]), 0.8493218002880191 / bw, W, wp,
+        kde1d_f32_win<NW>(dxw, dn, G, eg[0], ustep, 0.5 * (eg[0] + eg[G - 1]), 0.8493218002880191 / bw, W, wp,
                             norm * 0.3989422804014327 / bw, summ, win, crs, reinterpret_cast<double*>(part), dens);
       } else {
-        kde_inplace(dxw, dn, eg, G, bw, W, a.kernel, norm, part, F_NW * Nz, dens, ustep);
+        kde_inplace<NT>(dxw, dn, eg, G, bw, W, a.kernel, norm, part, NW * Nz, dens, ustep);
       }
       __syncthreads();
       // p_gw on the event grid (likelihood.py:139-141).  When nothing else needs the array, the interpolated value
@@ -547,35 +553,35 @@ numerator_f32_kernel(const NumArgs a) {
       };
       if (fused_tail) {
         if (a.kind == CHB_PGW_1D) {
-          for (int k = tid; k < Nz; k += F_NT) like_acc += pgw_at(k) * dV[k] * ck[k];
+          for (int k = tid; k < Nz; k += NT) like_acc += pgw_at(k) * dV[k] * ck[k];
         } else {
           const double* A = a.catA + (size_t)ev * Nz;
           const double* Bk = a.catB + (size_t)ev * Nz;
-          for (int k = tid; k < Nz; k += F_NT) {
+          for (int k = tid; k < Nz; k += NT) {
             const double pgs = has_cat ? fR * A[k] + (1.0 - pcompl_ev[k]) * dV[k] * Bk[k] : dV[k] * Bk[k];
             like_acc += pgw_at(k) * pgs * ck[k];
           }
         }
       } else {
-      for (int k = tid; k < Nz; k += F_NT) pgw[k] = pgw_at(k);
+      for (int k = tid; k < Nz; k += NT) pgw[k] = pgw_at(k);
       __syncthreads();
       if (a.kind == CHB_PGW_1D) {
-        for (int k = tid; k < Nz; k += F_NT) {
+        for (int k = tid; k < Nz; k += NT) {
           like_acc += pgw[k] * dV[k] * ck[k];
           if (pout) pout[k] = pgw[k];
         }
       } else {
         const double* gwp = a.gw_pdf + (size_t)ev * Pp;
-        if (pout) for (int i = tid; i < Pp * Nz; i += F_NT) pout[i] = pgw[i % Nz] * gwp[i / Nz];
+        if (pout) for (int i = tid; i < Pp * Nz; i += NT) pout[i] = pgw[i % Nz] * gwp[i / Nz];
         if (a.catA) {
           const double* A = a.catA + (size_t)ev * Nz;
           const double* Bk = a.catB + (size_t)ev * Nz;
-          for (int k = tid; k < Nz; k += F_NT) {
+          for (int k = tid; k < Nz; k += NT) {
             const double pgs = has_cat ? fR * A[k] + (1.0 - pcompl_ev[k]) * dV[k] * Bk[k] : dV[k] * Bk[k];
             like_acc += pgw[k] * pgs * ck[k];
           }
         } else {
-          for (int i = tid; i < npix * Nz; i += F_NT) {
+          for (int i = tid; i < npix * Nz; i += NT) {
             const int p = i / Nz, k = i - p * Nz;
             const double pc = has_cat ? pcat_ev[(size_t)p * Nz + k] : 0.0;
             if (pc == -100.0) continue;
@@ -589,16 +595,16 @@ numerator_f32_kernel(const NumArgs a) {
       // ---- p_gw3dmarg: per pixel, always Epanechnikov (likelihood.py:160-205) -----------------
       const int* off = a.pix_off + (size_t)ev * (Pp + 2);
       const double* gwp = a.gw_pdf + (size_t)ev * Pp;
-      if (pout) for (int i = tid; i < Pp * Nz; i += F_NT) pout[i] = 0.0;
+      if (pout) for (int i = tid; i < Pp * Nz; i += NT) pout[i] = 0.0;
       for (int p = 0; p < npix; ++p) {
         const int o0 = off[p], o1 = off[p + 1], nin = o1 - o0;
         Stats6 t = {0.0, 0.0, 0.0, 0.0, INFINITY, -INFINITY};
-        for (int j = o0 + tid; j < o1; j += F_NT) {
+        for (int j = o0 + tid; j < o1; j += NT) {
           const float2 v = zw[j];
           const double z = (double)v.x, w = (double)v.y;
           t.a += w; t.b += w * w; t.c += z; t.d += z * z; t.mx = fmaxf(t.mx, v.x);
         }
-        t = block_stats(t, red);
+        t = block_stats<NW>(t, red);
         double W = t.a, Q = t.b;
         const double zmax_in = fmax((double)t.mx, zmn);
         float2* dxw = zw + o0;
@@ -606,26 +612,26 @@ numerator_f32_kernel(const NumArgs a) {
         double dstd;
         if (a.binning) {
           const double step = (zmax_in - zmn) / (double)B;
-          for (int i = tid; i < B; i += F_NT) {
+          for (int i = tid; i < B; i += NT) {
             double e0 = __dadd_rn(__dmul_rn((double)i, step), zmn);
             double e1 = (i + 1 == B) ? zmax_in : __dadd_rn(__dmul_rn((double)(i + 1), step), zmn);
             bc[i] = (e0 + e1) / 2;
             bs[i] = 0.0;
           }
           __syncthreads();
-          for (int j = o0 + tid; j < o1; j += F_NT) {
+          for (int j = o0 + tid; j < o1; j += NT) {
             const float2 v = zw[j];
             double f = floor(((double)v.x - zmn) / (zmax_in - zmn) * B);
             if (!isnan(f)) atomicAdd(&bs[(int)fmin(fmax(f, 0.0), (double)(B - 1))], (double)v.y);
           }
           __syncthreads();
           Stats6 u = {0.0, 0.0, 0.0, 0.0, 0.f, 0.f};
-          for (int i = tid; i < B; i += F_NT) { u.a += bs[i]; u.b += bs[i] * bs[i]; u.c += bc[i]; u.d += bc[i] * bc[i]; }
-          u = block_stats(u, red);
+          for (int i = tid; i < B; i += NT) { u.a += bs[i]; u.b += bs[i] * bs[i]; u.c += bc[i]; u.d += bc[i] * bc[i]; }
+          u = block_stats<NW>(u, red);
           W = u.a; Q = u.b;
           const double cmean = u.c / B;
           dstd = sqrt(fmax(u.d / B - cmean * cmean, 0.0));
-          for (int i = tid; i < B; i += F_NT) xwb[i] = make_float2((float)bc[i], (float)bs[i]);
+          for (int i = tid; i < B; i += NT) xwb[i] = make_float2((float)bc[i], (float)bs[i]);
           dxw = xwb; dn = B;
           __syncthreads();
         } else {
@@ -641,9 +647,9 @@ numerator_f32_kernel(const NumArgs a) {
         else if (a.bw_method == CHB_BW_SILVERMAN) bw = pow(neff_k * 3.0 / 4.0, -0.2) * dstd;
         else bw = a.bw_value * dstd;
         const double scale = (W != 0.0) ? (norm * gwp[p]) : nan("");
-        kde_inplace(dxw, dn, eg, G, bw, W, CHB_KERNEL_EPAN, 1.0, part, F_NW * Nz, dens);
+        kde_inplace<NT>(dxw, dn, eg, G, bw, W, CHB_KERNEL_EPAN, 1.0, part, NW * Nz, dens);
         __syncthreads();
-        for (int k = tid; k < Nz; k += F_NT) {
+        for (int k = tid; k < Nz; k += NT) {
           const double raw = interp_lr(zgrid[k], eg, dens, G, 0.0, 0.0);
           const bool inside = (zgrid[k] >= eg[0] && zgrid[k] <= eg[G - 1]);
           const double v = inside ? raw * scale : 0.0;
@@ -667,10 +673,10 @@ numerator_f32_kernel(const NumArgs a) {
       else if (a.bw_method == CHB_BW_SILVERMAN) factor = pow(neff_k * 5.0 / 4.0, -1.0 / 7.0);
       else factor = a.bw_value;
       double m0 = 0, m1 = 0, m2 = 0;
-      for (int j = tid; j < Ns; j += F_NT) { const float2 v = zw[j]; double wn = (double)v.y / W; m0 += wn * (double)v.x; m1 += wn * ra[j]; m2 += wn * dec[j]; }
+      for (int j = tid; j < Ns; j += NT) { const float2 v = zw[j]; double wn = (double)v.y / W; m0 += wn * (double)v.x; m1 += wn * ra[j]; m2 += wn * dec[j]; }
       m0 = block_sum(m0, red); m1 = block_sum(m1, red); m2 = block_sum(m2, red);
       double c00 = 0, c01 = 0, c02 = 0, c11 = 0, c12 = 0, c22 = 0;
-      for (int j = tid; j < Ns; j += F_NT) {
+      for (int j = tid; j < Ns; j += NT) {
         const float2 v = zw[j];
         double wn = (double)v.y / W, r0 = (double)v.x - m0, r1 = ra[j] - m1, r2 = dec[j] - m2;
         c00 += wn * r0 * r0; c01 += wn * r0 * r1; c02 += wn * r0 * r2;
@@ -696,13 +702,13 @@ numerator_f32_kernel(const NumArgs a) {
       __syncthreads();
       const double l00 = L[0], l10 = L[1], l11 = L[2], l20 = L[3], l21 = L[4], l22 = L[5], lognorm = L[6];
       const double ps = 0.8493218002880191;            // sqrt(log2(e)/2)
-      for (int j = tid; j < Ns; j += F_NT) {
+      for (int j = tid; j < Ns; j += NT) {
         const float2 v = zw[j];
         const double r0 = (double)v.x - m0, r1 = ra[j] - m1, r2 = dec[j] - m2;
         yw[j] = make_float4((float)((r0 * l00 + r1 * l10 + r2 * l20) * ps), (float)((r1 * l11 + r2 * l21) * ps),
                             (float)((r2 * l22) * ps), (float)((double)v.y / W));
       }
-      if (pout) for (int i = tid; i < Pp * Nz; i += F_NT) pout[i] = 0.0;
+      if (pout) for (int i = tid; i < Pp * Nz; i += NT) pout[i] = 0.0;
       const double zlo = zmn - a.cut_grid * zstd, zhi = zmx + a.cut_grid * zstd;   // likelihood.py:225
       int* kmask = reinterpret_cast<int*>(dens);
       if (tid == 0) {
@@ -718,7 +724,7 @@ numerator_f32_kernel(const NumArgs a) {
       constexpr int FR = 2;
       const double enorm = exp(lognorm) * norm;
       const int ntiles = (npts + 32 * FR - 1) / (32 * FR);
-      for (int t = warp; t < ntiles; t += F_NW) {
+      for (int t = warp; t < ntiles; t += NW) {
         float q0[FR], q1[FR], q2[FR], acc[FR];
         int pk[FR];
 #pragma unroll
@@ -769,7 +775,7 @@ numerator_f32_kernel(const NumArgs a) {
       if (tid == 0) {
         double like = 0.0;
 #pragma unroll
-        for (int w = 0; w < F_NW; ++w) like += red[w];
+        for (int w = 0; w < NW; ++w) like += red[w];
         a.log_like[(size_t)h * a.Nev + ev] = nan_to_num_log_f(like); a.like_raw[(size_t)h * a.Nev + ev] = like;
       }
     }
@@ -782,15 +788,15 @@ static inline int kind_group(int kind) { return kind == CHB_PGW_MARG ? 1 : (kind
 // dispatch over (kind group, mode) -> kernel instantiation
 #define CHB_F32_DISPATCH(KG_, MODE_, EXPR)                                                     \
   switch ((KG_) * 3 + (MODE_)) {                                                               \
-    case 0: { auto kern = numerator_f32_kernel<0, 0>; EXPR; } break;                           \
-    case 1: { auto kern = numerator_f32_kernel<0, 1>; EXPR; } break;                           \
-    case 2: { auto kern = numerator_f32_kernel<0, 2>; EXPR; } break;                           \
-    case 3: { auto kern = numerator_f32_kernel<1, 0>; EXPR; } break;                           \
-    case 4: { auto kern = numerator_f32_kernel<1, 1>; EXPR; } break;                           \
-    case 5: { auto kern = numerator_f32_kernel<1, 2>; EXPR; } break;                           \
-    case 6: { auto kern = numerator_f32_kernel<2, 0>; EXPR; } break;                           \
-    case 7: { auto kern = numerator_f32_kernel<2, 1>; EXPR; } break;                           \
-    default: { auto kern = numerator_f32_kernel<2, 2>; EXPR; } break;                          \
+    case 0: { auto kern = numerator_f32_kernel<0, 0, F_NT>; EXPR; } break;                           \
+    case 1: { auto kern = numerator_f32_kernel<0, 1, F_NT>; EXPR; } break;                           \
+    case 2: { auto kern = numerator_f32_kernel<0, 2, F_NT>; EXPR; } break;                           \
+    case 3: { auto kern = numerator_f32_kernel<1, 0, F_NT>; EXPR; } break;                           \
+    case 4: { auto kern = numerator_f32_kernel<1, 1, F_NT>; EXPR; } break;                           \
+    case 5: { auto kern = numerator_f32_kernel<1, 2, F_NT>; EXPR; } break;                           \
+    case 6: { auto kern = numerator_f32_kernel<2, 0, F_NT>; EXPR; } break;                           \
+    case 7: { auto kern = numerator_f32_kernel<2, 1, F_NT>; EXPR; } break;                           \
+    default: { auto kern = numerator_f32_kernel<2, 2, F_NT>; EXPR; } break;                          \
   }
 cudaError_t numerator_f32_configure(int kind, int mode, size_t smem) {
   cudaError_t e = cudaSuccess;
