@@ -461,8 +461,21 @@ static int eval_impl(chb_handle* h, int64_t n_hyper, const double* d_hyper, doub
             h->num_grid = g2;
             b.prof = nullptr;
             CU(launch_numerator_f32(b, 1, g1, fs1, s), "reweight_f32 launch");
-            if (h->want_prof) { CU(h->prof.alloc((size_t)g2 * 8), "alloc profile"); b.prof = h->prof.p; }
-            CU(launch_numerator_f32(b, 2, g2, fs2, s), "kde_f32 launch");
+            // experimental (CHB_K2_VARIANT=1, 1-D kinds): 4-warp CTAs that keep the samples in global memory (MODE 3)
+            int kmode = 2, gk = g2;
+            size_t fsk = fs2;
+            { const char* e = getenv("CHB_K2_VARIANT");
+              if (e && e[0] == '1' && (c.kind_p_gw == CHB_PGW_1D || c.kind_p_gw == CHB_PGW_APPROX)) {
+                const size_t fs3 = numerator_f32_smem_bytes(a, 3);
+                if (numerator_f32_configure(a.kind, 3, fs3) == cudaSuccess) {
+                  const int per3 = numerator_f32_ctas_per_sm(a.kind, 3, fs3);
+                  if (per3 >= 1) { kmode = 3; fsk = fs3; gk = (int)std::min<long long>(ub, (long long)h->sm_count * per3); }
+                }
+                cudaGetLastError();
+              } }
+            h->num_grid = gk;
+            if (h->want_prof) { CU(h->prof.alloc((size_t)gk * 8), "alloc profile"); b.prof = h->prof.p; }
+            CU(launch_numerator_f32(b, kmode, gk, fsk, s), "kde_f32 launch");
             h->launches += 2;
           }
           h->launches--;                           // the common `launches++` below counts one of them

@@ -120,7 +120,7 @@ __device__ __forceinline__ void rs_reduce(float (&a)[N], int lane, int& rbase, b
   }
 }
 
-template <int R, int LPS>
+template <int R, int LPS, bool GL>
 __device__ __forceinline__ void kde_win_pass(const float2* __restrict__ xl, int cb, int ce, int gb, int glast,
                                              float4 sm4, double gfirst, double hd, float h,
                                              const float* __restrict__ cr, double* __restrict__ row) {
@@ -148,7 +148,7 @@ __device__ __forceinline__ void kde_win_pass(const float2* __restrict__ xl, int 
   for (int r = 0; r < R; ++r) acc2[r] = 0ull;
 #pragma unroll 2
   for (int jp = (cb >> 1) + sub; jp < (ce >> 1); jp += S) {
-    const float4 v = xp[jp];
+    const float4 v = GL ? __ldcg(xp + jp) : xp[jp];                    // GL: samples in global memory, read through L2
     const f32x2 nd = add2(pk2(v.x, v.y), gpn2);                        // x' - g = -d, both samples
     const f32x2 arg = add2(fma2(mul2(nd, nd), mone2, pk2(v.z, v.w)), Kp2);  // lw - d^2 + K
     const f32x2 qa = fma2(nd, p2h2, mh22);                             // -(2 hs d + h^2)
@@ -190,7 +190,7 @@ __device__ __forceinline__ void kde_win_pass(const float2* __restrict__ xl, int 
 // inclusive prefix sum of passes (pend), so a warp finds the chunk of list item `it` with one ballot.  Warp w
 // takes the contiguous slice [w T/NW, (w+1) T/NW) of the list: the extra passes of the wide edge chunks are
 // spread over the warps and the split is the same on every run (bit-reproducible sums).
-template <int R, int LPS, int NW>
+template <int R, int LPS, int NW, bool GL>
 __device__ __forceinline__ void kde_win_chunks(const float2* __restrict__ xl, int n, int G, double gfirst, double hd,
                                                const WinPlan& pl, const float4* __restrict__ summ, int2 w, int np,
                                                int pend, const float* __restrict__ cr, double* __restrict__ rows) {
@@ -206,7 +206,7 @@ __device__ __forceinline__ void kde_win_chunks(const float2* __restrict__ xl, in
     const int first = __shfl_sync(0xffffffffu, pend - np, c);
     const int gb = wx + (it - first) * W;
     const int cb = c * pl.chunk, ce = min(n, cb + pl.chunk);
-    kde_win_pass<R, LPS>(xl, cb, ce, gb, wy, summ[c], gfirst, hd, h, cr, row);
+    kde_win_pass<R, LPS, GL>(xl, cb, ce, gb, wy, summ[c], gfirst, hd, h, cr, row);
     __syncwarp();
   }
 }
@@ -214,7 +214,7 @@ __device__ __forceinline__ void kde_win_chunks(const float2* __restrict__ xl, in
 // Whole-CTA call (NW warps).  xw: in {x, w} (x sorted or not, n EVEN), out pairs {x'_a, x'_b, log2 w'_a, log2 w'_b}.  Scratch: summ/win hold
 // pl.nchunks (<= 32) entries, cr 16 floats, rows NW*G doubles.  dens[g] = scale * sum_j w'_j 2^-(g'_g - x'_j)^2 with
 // g'_g = (lb + g step - c) sf, sf = float(s) shared by samples and grid.
-template <int NW>
+template <int NW, bool GL = false>
 __device__ __forceinline__ void kde1d_f32_win(float2* __restrict__ xw, int n, int G, double lb, double step, double c,
                                               double s, double W, const WinPlan& pl, double scale,
                                               float4* __restrict__ summ, int2* __restrict__ win, float* __restrict__ cr,
@@ -277,7 +277,7 @@ __device__ __forceinline__ void kde1d_f32_win(float2* __restrict__ xw, int n, in
   int pend = np;                                                       // inclusive prefix sum of passes per chunk
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, pend, o); if (lane >= o) pend += y; }
-#define CHB_WIN_CASE(RR, LL) case RR * 16 + LL: kde_win_chunks<RR, LL, NW>(xw, n, G, gfirst, hd, pl, summ, w, np, pend, cr, rows); break;
+#define CHB_WIN_CASE(RR, LL) case RR * 16 + LL: kde_win_chunks<RR, LL, NW, GL>(xw, n, G, gfirst, hd, pl, summ, w, np, pend, cr, rows); break;
   switch (pl.R * 16 + pl.LPS) {
     CHB_WIN_CASE(4, 2) CHB_WIN_CASE(4, 4) CHB_WIN_CASE(4, 8)
     CHB_WIN_CASE(8, 2) CHB_WIN_CASE(8, 4) CHB_WIN_CASE(8, 8)

@@ -40,11 +40,12 @@
 struct FPlan {
   int tab, zgrid, dV, ck, pgw, eg, dens, bc, bs, xwb, part, red, stage, total;
 };
-// mode 0: fused kernel; 1: reweighting only (table + reduction scratch); 2: KDE + z-integral on staged samples (no table)
+// mode 0: fused kernel; 1: reweighting only (table + reduction scratch); 2: KDE + z-integral on staged samples (no table);
+// 3: like 2, but the samples stay in global memory (no shared-memory stage; 4-warp CTAs, experimental)
 __host__ __device__ inline FPlan make_fplan(int tab_doubles, int Nz, int B, int Ns, int kind, int mode = 0, int nw = F_NW) {
   FPlan p;
   int o = 0;
-  p.tab = o; o += (mode == 2) ? 0 : tab_doubles;
+  p.tab = o; o += (mode >= 2) ? 0 : tab_doubles;
   if (mode == 1) {
     p.zgrid = p.dV = p.ck = p.eg = p.pgw = p.dens = p.bc = p.bs = p.xwb = p.part = o;
     p.red = o; o += 64;
@@ -63,14 +64,16 @@ __host__ __device__ inline FPlan make_fplan(int tab_doubles, int Nz, int B, int 
   p.part = o; o += (nw * Nz + 1) / 2;
   p.red = o; o += 64;
   o = (o + 1) & ~1;
-  p.stage = o; o += (kind == CHB_PGW_FULL ? 3 : 1) * Ns;     // float2 {z,w} [+ float4 whitened]
+  p.stage = o; o += (mode == 3) ? 0 : (kind == CHB_PGW_FULL ? 3 : 1) * Ns;     // float2 {z,w} [+ float4 whitened]
   p.total = o;
   return p;
 }
 static inline int f32_tab_doubles(const TableLayout& lay) { return lay.f32_total() - lay.f32_dl4(); }
 
+#define F3_NT 128            // threads per CTA of the MODE 3 variant
 size_t numerator_f32_smem_bytes(const NumArgs& a, int mode) {
-  return (size_t)make_fplan(f32_tab_doubles(a.mc.lay), a.Nz, a.binning ? a.num_bins : 0, a.Ns, a.kind, mode).total * sizeof(double);
+  return (size_t)make_fplan(f32_tab_doubles(a.mc.lay), a.Nz, a.binning ? a.num_bins : 0, a.Ns, a.kind, mode,
+                            mode == 3 ? F3_NT / 32 : F_NW).total * sizeof(double);
 }
 
 __device__ __forceinline__ double nan_to_num_log_f(double like) {
@@ -252,8 +255,8 @@ numerator_f32_kernel(const NumArgs a) {
     fence_proxy_async();
     __syncthreads();
     const double* tblk = a.tabs + (size_t)h * lay.total() + lay.off_f32();
-    float2* zw = (MODE == 1) ? a.zw_stage + (size_t)unit * Ns : zw_s;
-    if (tid == 0) {
+    float2* zw = (MODE == 1 || MODE == 3) ? a.zw_stage + (size_t)unit * Ns : zw_s;
+    if (tid == 0 && MODE != 3) {
       if (MODE != 2) {
         mbar_expect_tx(&bar, tab_bytes);
         bulk_g2s(tab, tblk + lay.f32_dl4(), tab_bytes, &bar);
@@ -271,7 +274,7 @@ numerator_f32_kernel(const NumArgs a) {
     __syncthreads();
 
     // constants of the fast path; table pointers: dl4|cd4|lut in shared memory (global in MODE 2), zi4 in L2
-    F32Consts fc = make_f32_consts(a.mc, P, HC, (MODE == 2) ? tblk : tab - lay.f32_dl4());
+    F32Consts fc = make_f32_consts(a.mc, P, HC, (MODE >= 2) ? tblk : tab - lay.f32_dl4());
     fc.zi4 = reinterpret_cast<const float4*>(tblk + lay.f32_zi4());
     const CosmoRateF32 cr = make_cosmo_rate_f32(a.mc, P, HC);
     const float z_top = (float)P[CHB_P_ZMAX];
@@ -295,18 +298,20 @@ numerator_f32_kernel(const NumArgs a) {
     // MODE 2: the unit statistics written by the reweighting kernel are requested BEFORE waiting for the sample
     // copy, so their L2 latency hides behind the TMA instead of sitting in front of the next barrier
     double s1 = 0.0, s2 = 0.0, zmn = 0.0, zmx = 0.0, zstd = 0.0;
-    if (MODE == 2) {
+    if (MODE >= 2) {
       const double2* us = reinterpret_cast<const double2*>(a.unit_stats + (size_t)unit * 8);
       const double2 u0 = __ldg(us), u1 = __ldg(us + 1);
       s1 = u0.x; s2 = u0.y; zmn = u1.x; zmx = u1.y; zstd = __ldg(a.unit_stats + (size_t)unit * 8 + 4);
     }
     FPHASE(1);
-    mbar_wait(&bar, phase);
-    phase ^= 1;
+    if (MODE != 3) {
+      mbar_wait(&bar, phase);
+      phase ^= 1;
+    }
     FPHASE(0);
 
     const size_t so = (size_t)ev * Ns;
-    if (MODE != 2) {
+    if (MODE < 2) {
       fc.cd4_last = fc.cd4[fc.rm - 1];
       // ---- stage 1: reweighting (pop_wrapper.py:67-80) ------------------------------------------
       Stats6 st = {0.0, 0.0, 0.0, 0.0, INFINITY, -INFINITY};
@@ -528,7 +533,7 @@ numerator_f32_kernel(const NumArgs a) {
         const WinPlan wp = sh_wp;
         float4* summ = reinterpret_cast<float4*>(pgw);
         int2* win = reinterpret_cast<int2*>(summ + 32);
-        kde1d_f32_win<NW>(dxw, dn, G, eg[0], ustep, 0.5 * (eg[0] + eg[G - 1]), 0.8493218002880191 / bw, W, wp,
+        kde1d_f32_win<NW, MODE == 3>(dxw, dn, G, eg[0], ustep, 0.5 * (eg[0] + eg[G - 1]), 0.8493218002880191 / bw, W, wp,
                             norm * 0.3989422804014327 / bw, summ, win, crs, reinterpret_cast<double*>(part), dens);
       } else {
         kde_inplace<NT>(dxw, dn, eg, G, bw, W, a.kernel, norm, part, NW * Nz, dens, ustep);
@@ -800,17 +805,26 @@ static inline int kind_group(int kind) { return kind == CHB_PGW_MARG ? 1 : (kind
   }
 cudaError_t numerator_f32_configure(int kind, int mode, size_t smem) {
   cudaError_t e = cudaSuccess;
+  if (mode == 3) return cudaFuncSetAttribute(numerator_f32_kernel<0, 3, F3_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   CHB_F32_DISPATCH(kind_group(kind), mode, e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   return e;
 }
 int numerator_f32_ctas_per_sm(int kind, int mode, size_t smem) {
   int n = 0;
   cudaError_t e = cudaSuccess;
+  if (mode == 3) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, numerator_f32_kernel<0, 3, F3_NT>, F3_NT, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+  }
   CHB_F32_DISPATCH(kind_group(kind), mode, e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, F_NT, smem));
   if (e != cudaSuccess) { cudaGetLastError(); return 0; }
   return n;
 }
 cudaError_t launch_numerator_f32(const NumArgs& a, int mode, int grid, size_t smem, cudaStream_t s) {
+  if (mode == 3) {                              // 4-warp KDE variant: kind group 0 only
+    numerator_f32_kernel<0, 3, F3_NT><<<grid, F3_NT, smem, s>>>(a);
+    return cudaGetLastError();
+  }
   CHB_F32_DISPATCH(kind_group(a.kind), mode, (kern<<<grid, F_NT, smem, s>>>(a)));
   return cudaGetLastError();
 }
