@@ -35,7 +35,9 @@
 #pragma once
 #include "kde_f32.cuh"
 
-#define CHB_WIN_T2 30.0f          // terms below 2^-30 of the largest term at a grid point are dropped
+#ifndef CHB_WIN_T2
+#define CHB_WIN_T2 30.0f          // terms below 2^-30 of the largest term at a grid point are dropped (A/B: -DCHB_WIN_T2=24.0f)
+#endif
 #define CHB_WIN_MAXR 16
 #ifndef CHB_WIN_SPAN
 #define CHB_WIN_SPAN 5          // grid points allowed for the spread of a chunk when the tiling is chosen
