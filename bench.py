@@ -50,6 +50,7 @@ def parse():
   ap.add_argument("--nz", type=int, default=300)
   ap.add_argument("--hyper-side", type=int, default=16)
   ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--options", default="", help="per-handle tuning switches for A/B runs, e.g. 'fused=0,kde_win=0' (chb_set_option)")
   return ap.parse_args()
 
 
@@ -68,7 +69,11 @@ def build_workload(args, rank):
               z_range=np.array([0.073, 1.3]))
 
 
-def build_likelihood(w, fp_mode, distributed, kernel="gauss", binning=False):
+def parse_options(text):
+  return {k: float(v) for k, v in (kv.split("=") for kv in text.split(",") if kv)}
+
+
+def build_likelihood(w, fp_mode, distributed, kernel="gauss", binning=False, options=None):
   import chimera_b200 as cb
   ev = w["ev"]
   th = cb.theta_pe_det(**{k: ev[k] for k in ("m1det", "m2det", "dL", "pe_prior", "ra", "dec", "opt_nsides",
@@ -78,7 +83,8 @@ def build_likelihood(w, fp_mode, distributed, kernel="gauss", binning=False):
   pop = cb.population(cb.cosmo.flrw(H0=70., Om0=0.25, z_max=5.), cb.mass.plp(), cb.rate.madau_dickinson(), gal_cat=gcat)
   sel = cb.selection_function(cb.theta_inj_det(**w["inj"]), w["N_inj"], N_eff=5.)
   return cb.hyperlikelihood(th, w["zg"], pop, sel, kind_p_gw3d="approximate", kernel=kernel, binning=binning, num_bins=200,
-                            cut_grid=2.0, pe_neff=2.0, fp_mode=fp_mode, distributed=distributed, presharded=True)
+                            cut_grid=2.0, pe_neff=2.0, fp_mode=fp_mode, distributed=distributed, presharded=True,
+                            options=options)
 
 
 # ------------------------------------------------------------------------------------------ CPU oracle
@@ -254,7 +260,7 @@ def run_ours(args, rank, world, local_rank):
   # cold start: handle creation + one-time upload of every input from host buffers + the first evaluation
   torch.cuda.synchronize()
   t_cold = time.perf_counter()
-  like = build_likelihood(w, args.fp_mode, distributed=world > 1)
+  like = build_likelihood(w, args.fp_mode, distributed=world > 1, options=parse_options(args.options))
   like(**w["hyper"])
   torch.cuda.synchronize()
   cold_s = time.perf_counter() - t_cold
@@ -375,7 +381,7 @@ def run_ours(args, rank, world, local_rank):
     # the same workload with the reference's DEFAULT KDE options (Epanechnikov kernel, 200 bins),
     # for comparison only: 3 warm-up + 3 timed device-resident steps
     try:
-      like_d = build_likelihood(w, args.fp_mode, False, kernel="epan", binning=True)
+      like_d = build_likelihood(w, args.fp_mode, False, kernel="epan", binning=True, options=parse_options(args.options))
       for _ in range(3):
         like_d.partials_device(d_rows, d_part)
       torch.cuda.synchronize()

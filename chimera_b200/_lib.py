@@ -10,7 +10,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CHB_LIB") or os.path.join(_HERE, "libchimera_b200.so")     # CHB_LIB: A/B builds
 
-CHB_ABI_VERSION = 1
+CHB_ABI_VERSION = 2
 CHB_NPAR = 32
 OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 
@@ -53,6 +53,7 @@ EXPORTS = {
   "chb_last_error": (C.c_char_p, [_hp]),
   "chb_create": (C.c_int, [C.POINTER(_hp), C.POINTER(chb_config)]),
   "chb_destroy": (None, [_hp]),
+  "chb_set_option": (C.c_int, [_hp, C.c_char_p, C.c_double]),
   "chb_set_events": (C.c_int, [_hp, C.c_int64, C.c_int64, C.c_int64, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
   "chb_set_pixels": (C.c_int, [_hp, C.c_int64, _ip, _ip, _dp, _dp, _dp]),
   "chb_set_catalog": (C.c_int, [_hp, _dp, _dp]),

@@ -63,9 +63,17 @@ struct chb_handle {
   DevBuf<float2> zterms;
   DevBuf<float2> zw_stage;
   DevBuf<double> unit_stats;
-  int64_t plan_nh = -1, plan_nev = -1, plan_ns = -1, plan_nb = 0;
+  int64_t plan_nh = -1, plan_nb = 0;       // split-form plan, valid for plan_nh hyper-points (reset by chb_set_* / options)
   int plan_per1 = 0, plan_per2 = 0;
   bool plan_ok = false;
+  int fused_per = -1;                      // co-resident CTAs per SM of numerator_fused_kernel for the current shapes
+  // tuning / diagnostic options (chb_set_option); they never change what is computed, only how
+  int opt_fused = 1;                       // 1-D kinds, fp32: one fused kernel (numerator_fused.cu); 0: round-1 split kernels
+  int opt_split = 1;                       // round-1 path: split MODE 1 -> stage -> MODE 2 (0: one MODE 0 kernel)
+  int opt_kde_win = 32;                    // windowed recurrence: sub-stream iterations per chunk (0: windows off)
+  int opt_kde_direct = 0;                  // 1: one MUFU.EX2 per pair (no recurrence)
+  int opt_bin_runs = 1;                    // round-1 path: binning by runs of the sorted samples
+  double opt_stage_gb = 12.0;              // round-1 path: budget of the {z, w} stage buffer
   DevBuf<double> catA, catB;
   bool cat_collapsed = false;
   bool want_prof = false;
@@ -188,6 +196,7 @@ int chb_set_events(chb_handle* h, int64_t Nev, int64_t Ns, int64_t Nz, const dou
   if (ra && dec) { h->h_ra.assign(ra, ra + n); h->h_dec.assign(dec, dec + n); } else { h->h_ra.clear(); h->h_dec.clear(); }
   CU(h->zgrids.upload(z_grids, (size_t)Nev * Nz), "upload z_grids");
   h->have_events = true; h->have_pixels = false; h->have_catalog = false; h->dirty = true;
+  h->plan_nh = -1; h->fused_per = -1;
   return CHB_OK;
 }
 
@@ -218,6 +227,7 @@ int chb_set_pixels(chb_handle* h, int64_t P, const int64_t* pixels_opt_nsides, c
   }
   CU(h->neff_pix.upload(neff.data(), neff.size()), "upload neff_pixels");
   h->have_pixels = true; h->dirty = true;
+  h->plan_nh = -1; h->fused_per = -1;
   return CHB_OK;
 }
 
@@ -368,9 +378,8 @@ static int eval_impl(chb_handle* h, int64_t n_hyper, const double* d_hyper, doub
     a.kind = c.kind_p_gw; a.kernel = c.kernel; a.bw_method = c.bw_method; a.use_cut = c.use_cut_grid;
     a.binning = (c.kind_p_gw == CHB_PGW_FULL) ? 0 : c.binning; a.num_bins = c.num_bins; a.fp_mode = c.fp_mode;
     a.bw_value = c.bw_value; a.cut_grid = c.cut_grid; a.pe_neff = c.pe_neff;
-    { const char* e = getenv("CHB_KDE_DIRECT"); a.rec_off = (e && e[0] == '1') ? 1 : 0; }
-    { const char* e = getenv("CHB_BIN_RUNS"); a.bin_runs = (e && e[0] == '0') ? 0 : 1; }
-    { const char* e = getenv("CHB_KDE_WIN"); a.kde_win_iters = e ? atoi(e) : 32; if (!h->sorted) a.kde_win_iters = 0; }
+    a.rec_off = h->opt_kde_direct; a.bin_runs = h->opt_bin_runs;
+    a.kde_win_iters = h->sorted ? h->opt_kde_win : 0;
     a.Nev = (int)h->Nev; a.Ns = (int)h->Ns; a.Nz = (int)h->Nz; a.P = (int)std::max<int64_t>(h->P, 1);
     a.m1d = h->m1d.p; a.m2d = h->m2d.p; a.dL = h->dL.p; a.prior = h->prior.p; a.ra = h->ra.p; a.dec = h->dec.p;
     a.zgrids = h->zgrids.p; a.pix_off = h->pix_off.p; a.ra_pix = h->ra_pix.p; a.dec_pix = h->dec_pix.p;
@@ -399,20 +408,28 @@ static int eval_impl(chb_handle* h, int64_t n_hyper, const double* d_hyper, doub
     a.prof = nullptr;
     bool fast = false;
     if (c.fp_mode == CHB_FP32) {
-      // fast path: 256-thread CTAs, float2 staging.  Split form (default): reweighting kernel -> stage buffers in
-      // global memory -> KDE/z-integral kernel, three CTAs per SM each; fused form (CHB_SPLIT=0, odd Ns, or no
-      // memory for the stage): one kernel, two CTAs per SM.
+      // The dynamic-shared-memory attribute of a kernel is process-wide: it is only ever set to the device maximum
+      // (never to a handle's own footprint), so handles with different shapes cannot invalidate each other's launches.
+      const int optin = h->max_smem_optin;
+      // (1) 1-D kinds: ONE fused kernel per step (numerator_fused.cu), samples never leave shared memory.
+      const size_t ff = numerator_fused_smem_bytes(a);
+      bool fused = h->opt_fused && numerator_fused_supported(a) && ff <= (size_t)optin;
+      if (fused && h->fused_per < 0) {
+        h->fused_per = (numerator_fused_configure(optin) == cudaSuccess) ? numerator_fused_ctas_per_sm(ff) : 0;
+        cudaGetLastError();
+      }
+      if (fused && h->fused_per < 1) fused = false;
+      // (2) other kinds (and the A/B switch): split form -- reweighting kernel -> stage buffers in global memory ->
+      // KDE/z-integral kernel; fused MODE 0 kernel for odd Ns or when there is no memory for the stage.
       size_t fs = numerator_f32_smem_bytes(a, 0);
       const size_t fs1 = numerator_f32_smem_bytes(a, 1), fs2 = numerator_f32_smem_bytes(a, 2);
-      bool split = (h->Ns % 2 == 0) && fs2 <= (size_t)h->max_smem_optin && fs1 <= (size_t)h->max_smem_optin;
-      { const char* e = getenv("CHB_SPLIT"); if (e && e[0] == '0') split = false; }
+      bool split = !fused && h->opt_split && (h->Ns % 2 == 0) && fs2 <= (size_t)optin && fs1 <= (size_t)optin;
       int64_t nb = n_hyper;                        // hyper-points per batch of the split form
       if (split) {
-        // the plan (batch size, stage buffers, occupancy) is cached per (n_hyper, Nev, Ns): no driver queries
-        // inside the timed region of later evaluations
-        if (h->plan_nh != n_hyper || h->plan_nev != h->Nev || h->plan_ns != h->Ns) {
-          size_t budget = (size_t)12 << 30;
-          { const char* e = getenv("CHB_STAGE_GB"); if (e && atof(e) > 0) budget = (size_t)(atof(e) * (double)((size_t)1 << 30)); }
+        // the plan (batch size, stage buffers, occupancy) is cached per n_hyper and reset by chb_set_* / chb_set_option:
+        // no driver queries inside the timed region of later evaluations
+        if (h->plan_nh != n_hyper) {
+          const size_t budget = (size_t)(h->opt_stage_gb * (double)((size_t)1 << 30));
           const size_t per_h = (size_t)h->Nev * h->Ns * sizeof(float2);
           nb = std::max<int64_t>(1, std::min<int64_t>(n_hyper, (int64_t)(budget / per_h)));
           size_t free_b = 0, total_b = 0;
@@ -421,18 +438,18 @@ static int eval_impl(chb_handle* h, int64_t n_hyper, const double* d_hyper, doub
           h->plan_ok = false;
           if (h->zw_stage.alloc((size_t)nb * h->Nev * h->Ns) == cudaSuccess &&
               h->unit_stats.alloc((size_t)nb * h->Nev * 8) == cudaSuccess &&
-              numerator_f32_configure(a.kind, 1, fs1) == cudaSuccess && numerator_f32_configure(a.kind, 2, fs2) == cudaSuccess) {
+              numerator_f32_configure(a.kind, 1, optin) == cudaSuccess && numerator_f32_configure(a.kind, 2, optin) == cudaSuccess) {
             h->plan_per1 = numerator_f32_ctas_per_sm(a.kind, 1, fs1);
             h->plan_per2 = numerator_f32_ctas_per_sm(a.kind, 2, fs2);
             h->plan_ok = h->plan_per1 >= 1 && h->plan_per2 >= 1;
           }
           cudaGetLastError();
-          h->plan_nb = nb; h->plan_nh = n_hyper; h->plan_nev = h->Nev; h->plan_ns = h->Ns;
+          h->plan_nb = nb; h->plan_nh = n_hyper;
         }
         nb = h->plan_nb;
         split = h->plan_ok;
       }
-      if (split || fs <= (size_t)h->max_smem_optin) {
+      if (fused || split || fs <= (size_t)optin) {
         // z-grid terms for all (hyper-point, event, k) in one full-occupancy pass when they fit in 2 GiB
         const size_t zt_elems = (size_t)n_hyper * h->Nev * h->Nz;
         a.zterms = nullptr; a.zterms_out = nullptr; a.zterms_h0 = 0;
@@ -443,7 +460,12 @@ static int eval_impl(chb_handle* h, int64_t n_hyper, const double* d_hyper, doub
           h->launches++;
           a.zterms = h->zterms.p;
         }
-        if (split) {
+        if (fused) {
+          const int grid = (int)std::min<long long>(units, (long long)h->sm_count * h->fused_per);
+          h->num_grid = grid; h->num_smem = ff;
+          CU(launch_numerator_fused(a, grid, ff, s), "numerator_fused launch");
+          fast = true;
+        } else if (split) {
           const int per1 = h->plan_per1, per2 = h->plan_per2;
           h->num_smem = fs2;
           for (int64_t h0 = 0; h0 < n_hyper; h0 += nb) {
@@ -461,27 +483,14 @@ static int eval_impl(chb_handle* h, int64_t n_hyper, const double* d_hyper, doub
             h->num_grid = g2;
             b.prof = nullptr;
             CU(launch_numerator_f32(b, 1, g1, fs1, s), "reweight_f32 launch");
-            // experimental (CHB_K2_VARIANT=1, 1-D kinds): 4-warp CTAs that keep the samples in global memory (MODE 3)
-            int kmode = 2, gk = g2;
-            size_t fsk = fs2;
-            { const char* e = getenv("CHB_K2_VARIANT");
-              if (e && e[0] == '1' && (c.kind_p_gw == CHB_PGW_1D || c.kind_p_gw == CHB_PGW_APPROX)) {
-                const size_t fs3 = numerator_f32_smem_bytes(a, 3);
-                if (numerator_f32_configure(a.kind, 3, fs3) == cudaSuccess) {
-                  const int per3 = numerator_f32_ctas_per_sm(a.kind, 3, fs3);
-                  if (per3 >= 1) { kmode = 3; fsk = fs3; gk = (int)std::min<long long>(ub, (long long)h->sm_count * per3); }
-                }
-                cudaGetLastError();
-              } }
-            h->num_grid = gk;
-            if (h->want_prof) { CU(h->prof.alloc((size_t)gk * 8), "alloc profile"); b.prof = h->prof.p; }
-            CU(launch_numerator_f32(b, kmode, gk, fsk, s), "kde_f32 launch");
+            if (h->want_prof) { CU(h->prof.alloc((size_t)g2 * 8), "alloc profile"); b.prof = h->prof.p; }
+            CU(launch_numerator_f32(b, 2, g2, fs2, s), "kde_f32 launch");
             h->launches += 2;
           }
           h->launches--;                           // the common `launches++` below counts one of them
           fast = true;
         } else {
-          CU(numerator_f32_configure(a.kind, 0, fs), "numerator_f32 smem opt-in");
+          CU(numerator_f32_configure(a.kind, 0, optin), "numerator_f32 smem opt-in");
           int per_sm = numerator_f32_ctas_per_sm(a.kind, 0, fs);
           if (per_sm >= 1) {
             int grid = (int)std::min<long long>(units, (long long)h->sm_count * per_sm);
@@ -534,6 +543,20 @@ static int eval_impl(chb_handle* h, int64_t n_hyper, const double* d_hyper, doub
                    d_partials, s), "reduce launch");
   h->launches++;
   cudaEventRecord(h->ev[4], s);
+  return CHB_OK;
+}
+
+int chb_set_option(chb_handle* h, const char* name, double value) {
+  if (!h || !name) return CHB_ERR_INVALID;
+  const std::string n(name);
+  if (n == "fused") h->opt_fused = value != 0.0;
+  else if (n == "split") h->opt_split = value != 0.0;
+  else if (n == "kde_win") { if (value < 0 || value > 4096) return fail(h, CHB_ERR_INVALID, "kde_win out of range"); h->opt_kde_win = (int)value; }
+  else if (n == "kde_direct") h->opt_kde_direct = value != 0.0;
+  else if (n == "bin_runs") h->opt_bin_runs = value != 0.0;
+  else if (n == "stage_gb") { if (!(value > 0.0)) return fail(h, CHB_ERR_INVALID, "stage_gb must be positive"); h->opt_stage_gb = value; }
+  else return fail(h, CHB_ERR_INVALID, "unknown option '" + n + "'");
+  h->plan_nh = -1; h->fused_per = -1;
   return CHB_OK;
 }
 

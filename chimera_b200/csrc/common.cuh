@@ -82,6 +82,11 @@ size_t numerator_f32_smem_bytes(const NumArgs& a, int mode);
 cudaError_t numerator_f32_configure(int kind, int mode, size_t smem);
 int numerator_f32_ctas_per_sm(int kind, int mode, size_t smem);
 cudaError_t launch_numerator_f32(const NumArgs& a, int mode, int grid, size_t smem, cudaStream_t s);
+size_t numerator_fused_smem_bytes(const NumArgs& a);
+bool numerator_fused_supported(const NumArgs& a);
+cudaError_t numerator_fused_configure(size_t smem);
+int numerator_fused_ctas_per_sm(size_t smem);
+cudaError_t launch_numerator_fused(const NumArgs& a, int grid, size_t smem, cudaStream_t s);
 cudaError_t launch_zgrid_terms(const NumArgs& a, int h0, int nh, cudaStream_t s);
 cudaError_t launch_catalog_collapse(int Nev, int P, int Nz, const double* p_cat, const double* gw_pdf, const int* neff_pix,
                                    double* catA, double* catB, cudaStream_t s);

@@ -66,7 +66,9 @@ struct WinPlan { int R, LPS, chunk, nchunks; };
 // (+ the spread of a chunk) in ONE pass; the widest admissible tile when none does.  Evaluated by one thread per
 // unit, so it is a short table walk.  Returns false when windows cannot pay (window ~ whole grid, too few samples,
 // grid too coarse for the recurrence).
-__device__ __forceinline__ bool win_plan(int G, int n, float h, int iters, int max_chunks, WinPlan& pl) {
+// `gran`: chunk sizes are rounded up to a multiple of it (the fused kernel summarises 64-sample blocks while it
+// reweights them, so its chunks must be unions of such blocks).
+__device__ __forceinline__ bool win_plan(int G, int n, float h, int iters, int max_chunks, WinPlan& pl, int gran = 1) {
   if (!(h > 0.f) || h > 1.8f || iters <= 0) return false;
   const int wn = 2 * (int)ceilf(6.2f / h) + CHB_WIN_SPAN;
   if (10 * wn > 7 * G) return false;
@@ -87,6 +89,7 @@ __device__ __forceinline__ bool win_plan(int G, int n, float h, int iters, int m
   // at most 32 chunks (phase B keeps one chunk per lane), each a multiple of 4 sub-stream rounds
   const int q = 4 * (32 / pl.LPS);
   pl.chunk = max(iters * (32 / pl.LPS), ((n + 31) / 32 + q - 1) / q * q);
+  pl.chunk = (pl.chunk + gran - 1) / gran * gran;
   pl.nchunks = (n + pl.chunk - 1) / pl.chunk;
   (void)max_chunks;
   return pl.nchunks >= 8;
@@ -122,10 +125,14 @@ __device__ __forceinline__ void rs_reduce(float (&a)[N], int lane, int& rbase, b
   }
 }
 
-template <int R, int LPS, bool GL>
+// RAW: the stage holds UNSCALED samples {dz_a, dz_b, log2 w_a, log2 w_b}; the scale x' = dz * sf rides in the FFMA2 that
+// forms x' - g, the weight normalisation log2(1/W) = koff in the constant added to the exponent -- no rescaling pass
+// over the samples and no extra instruction in the loop.
+template <int R, int LPS, bool GL, bool RAW = false>
 __device__ __forceinline__ void kde_win_pass(const float2* __restrict__ xl, int cb, int ce, int gb, int glast,
                                              float4 sm4, double gfirst, double hd, float h,
-                                             const float* __restrict__ cr, double* __restrict__ row) {
+                                             const float* __restrict__ cr, double* __restrict__ row,
+                                             float sf = 1.f, float koff = 0.f) {
   static_assert(R % 4 == 0 && R <= CHB_WIN_MAXR, "run length");
   constexpr int S = 32 / LPS;
   const int lane = threadIdx.x & 31;
@@ -143,7 +150,8 @@ __device__ __forceinline__ void kde_win_pass(const float2* __restrict__ xl, int 
   // Samples are stored in pairs {x'_a, x'_b, lw_a, lw_b} (phase A): one LDS.128 brings two samples as two packed
   // operands, and the whole recurrence runs on FADD2 / FMUL2 / FFMA2 -- one issue slot for two samples.
   const float4* __restrict__ xp = reinterpret_cast<const float4*>(xl);
-  const f32x2 gpn2 = pk2(-gp, -gp), mone2 = pk2(-1.f, -1.f), Kp2 = pk2(Kf, Kf);
+  const f32x2 gpn2 = pk2(-gp, -gp), mone2 = pk2(-1.f, -1.f), Kp2 = pk2(Kf + koff, Kf + koff);
+  const f32x2 sf2 = pk2(sf, sf);
   const f32x2 p2h2 = pk2(-m2h, -m2h), mh22 = pk2(mh2, mh2);
   f32x2 acc2[R];
 #pragma unroll
@@ -151,7 +159,7 @@ __device__ __forceinline__ void kde_win_pass(const float2* __restrict__ xl, int 
 #pragma unroll 2
   for (int jp = (cb >> 1) + sub; jp < (ce >> 1); jp += S) {
     const float4 v = GL ? __ldcg(xp + jp) : xp[jp];                    // GL: samples in global memory, read through L2
-    const f32x2 nd = add2(pk2(v.x, v.y), gpn2);                        // x' - g = -d, both samples
+    const f32x2 nd = RAW ? fma2(pk2(v.x, v.y), sf2, gpn2) : add2(pk2(v.x, v.y), gpn2);   // x' - g = -d, both samples
     const f32x2 arg = add2(fma2(mul2(nd, nd), mone2, pk2(v.z, v.w)), Kp2);  // lw - d^2 + K
     const f32x2 qa = fma2(nd, p2h2, mh22);                             // -(2 hs d + h^2)
     float a0, a1, b0, b1;
@@ -192,10 +200,11 @@ __device__ __forceinline__ void kde_win_pass(const float2* __restrict__ xl, int 
 // inclusive prefix sum of passes (pend), so a warp finds the chunk of list item `it` with one ballot.  Warp w
 // takes the contiguous slice [w T/NW, (w+1) T/NW) of the list: the extra passes of the wide edge chunks are
 // spread over the warps and the split is the same on every run (bit-reproducible sums).
-template <int R, int LPS, int NW, bool GL>
+template <int R, int LPS, int NW, bool GL, bool RAW = false>
 __device__ __forceinline__ void kde_win_chunks(const float2* __restrict__ xl, int n, int G, double gfirst, double hd,
                                                const WinPlan& pl, const float4* __restrict__ summ, int2 w, int np,
-                                               int pend, const float* __restrict__ cr, double* __restrict__ rows) {
+                                               int pend, const float* __restrict__ cr, double* __restrict__ rows,
+                                               float sf = 1.f, float koff = 0.f) {
   constexpr int W = LPS * R;
   const int warp = threadIdx.x >> 5;
   const float h = (float)hd;
@@ -208,8 +217,60 @@ __device__ __forceinline__ void kde_win_chunks(const float2* __restrict__ xl, in
     const int first = __shfl_sync(0xffffffffu, pend - np, c);
     const int gb = wx + (it - first) * W;
     const int cb = c * pl.chunk, ce = min(n, cb + pl.chunk);
-    kde_win_pass<R, LPS, GL>(xl, cb, ce, gb, wy, summ[c], gfirst, hd, h, cr, row);
+    kde_win_pass<R, LPS, GL, RAW>(xl, cb, ce, gb, wy, summ[c], gfirst, hd, h, cr, row, sf, koff);
     __syncwarp();
+  }
+}
+
+// Phases B and C for chunk summaries that are already in `summ` (scaled units, weights normalised), rows zeroed and
+// `cr` filled; all of them visible to the CTA (a barrier has passed).  Ends with dens[] written (no barrier after).
+template <int NW, bool GL, bool RAW>
+__device__ __forceinline__ void kde_win_BC(const float2* __restrict__ xw, int n, int G, double gfirst, double hd,
+                                           const WinPlan& pl, double scale, const float4* __restrict__ summ,
+                                           int2* __restrict__ win, const float* __restrict__ cr,
+                                           double* __restrict__ rows, double* __restrict__ dens,
+                                           float sf = 1.f, float koff = 0.f) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float h = (float)hd;
+  // ---- phase B: lane c holds chunk c; every warp walks its share of the grid points: M(g) is one warp-wide max,
+  // the need test one compare per lane, the hull of the needed points accumulates in registers ------------
+  const float lgchunk = lg2f_((float)pl.chunk);
+  const float4 my = (lane < pl.nchunks) ? summ[lane] : make_float4(INFINITY, -INFINITY, -INFINITY, 0.f);
+  {
+    const float myU = my.z + lgchunk, gf = (float)gfirst;
+    int gmin = G, gmax = -1;
+    for (int g = warp; g < G; g += NW) {
+      const float gp = fmaf((float)g, h, gf);
+      const float d = gp - my.w;
+      const float m = warp_max_f32(fmaf(-d, d, my.z));
+      const float dist = fmaxf(fmaxf(my.x - gp, gp - my.y), 0.f);
+      if (fmaf(-dist, dist, myU) >= m - CHB_WIN_T2 && my.z > -INFINITY) { gmin = min(gmin, g); gmax = g; }
+    }
+    if (gmax >= 0) { atomicMin(&win[lane].x, gmin); atomicMax(&win[lane].y, gmax); }
+  }
+  __syncthreads();
+  // ---- phase C: pair sums ------------------------------------------------------------------------
+  const int Wp = pl.LPS * pl.R;
+  const int2 w = (lane < pl.nchunks) ? win[lane] : make_int2(G, -1);
+  const int np = (w.x <= w.y) ? (w.y - w.x + Wp) / Wp : 0;
+  int pend = np;                                                       // inclusive prefix sum of passes per chunk
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, pend, o); if (lane >= o) pend += y; }
+#define CHB_WIN_CASE(RR, LL) case RR * 16 + LL: kde_win_chunks<RR, LL, NW, GL, RAW>(xw, n, G, gfirst, hd, pl, summ, w, np, pend, cr, rows, sf, koff); break;
+  switch (pl.R * 16 + pl.LPS) {
+    CHB_WIN_CASE(4, 2) CHB_WIN_CASE(4, 4) CHB_WIN_CASE(4, 8)
+    CHB_WIN_CASE(8, 2) CHB_WIN_CASE(8, 4) CHB_WIN_CASE(8, 8)
+    CHB_WIN_CASE(12, 2) CHB_WIN_CASE(12, 4) CHB_WIN_CASE(12, 8)
+    CHB_WIN_CASE(16, 2) CHB_WIN_CASE(16, 4) CHB_WIN_CASE(16, 8)
+    default: break;
+  }
+#undef CHB_WIN_CASE
+  __syncthreads();
+  for (int g = threadIdx.x; g < G; g += NW * 32) {
+    double acc = 0.0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) acc += rows[w * G + g];
+    dens[g] = acc * scale;
   }
 }
 
@@ -255,44 +316,5 @@ __device__ __forceinline__ void kde1d_f32_win(float2* __restrict__ xw, int n, in
     }
   }
   __syncthreads();
-  // ---- phase B: lane c holds chunk c; every warp walks its share of the grid points: M(g) is one warp-wide max,
-  // the need test one compare per lane, the hull of the needed points accumulates in registers ------------
-  const float lgchunk = lg2f_((float)pl.chunk);
-  const float4 my = (lane < pl.nchunks) ? summ[lane] : make_float4(INFINITY, -INFINITY, -INFINITY, 0.f);
-  {
-    const float myU = my.z + lgchunk, gf = (float)gfirst;
-    int gmin = G, gmax = -1;
-    for (int g = warp; g < G; g += NW) {
-      const float gp = fmaf((float)g, h, gf);
-      const float d = gp - my.w;
-      const float m = warp_max_f32(fmaf(-d, d, my.z));
-      const float dist = fmaxf(fmaxf(my.x - gp, gp - my.y), 0.f);
-      if (fmaf(-dist, dist, myU) >= m - CHB_WIN_T2 && my.z > -INFINITY) { gmin = min(gmin, g); gmax = g; }
-    }
-    if (gmax >= 0) { atomicMin(&win[lane].x, gmin); atomicMax(&win[lane].y, gmax); }
-  }
-  __syncthreads();
-  // ---- phase C: pair sums ------------------------------------------------------------------------
-  const int Wp = pl.LPS * pl.R;
-  const int2 w = (lane < pl.nchunks) ? win[lane] : make_int2(G, -1);
-  const int np = (w.x <= w.y) ? (w.y - w.x + Wp) / Wp : 0;
-  int pend = np;                                                       // inclusive prefix sum of passes per chunk
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, pend, o); if (lane >= o) pend += y; }
-#define CHB_WIN_CASE(RR, LL) case RR * 16 + LL: kde_win_chunks<RR, LL, NW, GL>(xw, n, G, gfirst, hd, pl, summ, w, np, pend, cr, rows); break;
-  switch (pl.R * 16 + pl.LPS) {
-    CHB_WIN_CASE(4, 2) CHB_WIN_CASE(4, 4) CHB_WIN_CASE(4, 8)
-    CHB_WIN_CASE(8, 2) CHB_WIN_CASE(8, 4) CHB_WIN_CASE(8, 8)
-    CHB_WIN_CASE(12, 2) CHB_WIN_CASE(12, 4) CHB_WIN_CASE(12, 8)
-    CHB_WIN_CASE(16, 2) CHB_WIN_CASE(16, 4) CHB_WIN_CASE(16, 8)
-    default: break;
-  }
-#undef CHB_WIN_CASE
-  __syncthreads();
-  for (int g = threadIdx.x; g < G; g += NW * 32) {
-    double acc = 0.0;
-#pragma unroll
-    for (int w = 0; w < NW; ++w) acc += rows[w * G + g];
-    dens[g] = acc * scale;
-  }
+  kde_win_BC<NW, GL, false>(xw, n, G, gfirst, hd, pl, scale, summ, win, cr, rows, dens);
 }

@@ -34,6 +34,17 @@ enum {
   HC_LG2_Z1,        // log2(z_grid_interp[1]) = log2(1e-10)
   HC_INV_LG2_ZSTEP  // (rc-2) / (log2 z_max - log2 1e-10)
 };
+// single-precision constants of the fused fp32 kernel, one row of CHB_NFC floats per hyper-point (written by
+// build_tables_kernel next to the packed tables): normalisations are folded into log2 offsets so that a mass pdf
+// is one FFMA + one MUFU.EX2 and cannot leave the fp32 range before it is normalised.
+#define CHB_NFC 32
+enum {
+  FC_LG2_M0 = 0, FC_INV_LG2_MSTEP, FC_LO, FC_HI, FC_NEG_ALPHA, FC_BETA, FC_DM,
+  FC_KA,          // log2 of the factor of the first power law:  tpl/bpl 1/norm_p1;  plp (1-lambda)/(pl_norm norm_p1)
+  FC_KG,          // plp: log2(lambda / (sigma sqrt(2 pi) tg_norm norm_p1));  bpl: log2(ratio / norm_p1)
+  FC_MU, FC_G_HI, FC_G_C, FC_MB, FC_NEG_ALPHA2, FC_CDL_X, FC_CDL_Y, FC_LUT_B0 /* int bits */, FC_LUT_NB /* int bits */,
+  FC_Z_TOP
+};
 #define CHB_LUT_SHIFT 18      // 32 buckets per octave of dL: <= 1.4 knots per bucket, so <= 2 scan steps
 #define CHB_LUT_CAP 2048      // uint16 entries
 
@@ -235,7 +246,8 @@ struct TableLayout {
   __host__ __device__ int f32_dl4() const { return 2 * rcs; }
   __host__ __device__ int f32_cd4() const { return 4 * rcs; }
   __host__ __device__ int f32_lut() const { return 4 * rcs + 2 * rms; }
-  __host__ __device__ int f32_total() const { return 4 * rcs + 2 * rms + CHB_LUT_CAP / 4; }
+  __host__ __device__ int f32_fc() const { return 4 * rcs + 2 * rms + CHB_LUT_CAP / 4; }   // CHB_NFC floats (FC_* below)
+  __host__ __device__ int f32_total() const { return 4 * rcs + 2 * rms + CHB_LUT_CAP / 4 + CHB_NFC / 2; }
   __host__ __device__ int total() const { return f64_total() + f32_total(); }
 };
 static inline TableLayout make_layout(int rc, int rm) {

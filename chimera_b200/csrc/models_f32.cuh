@@ -114,8 +114,8 @@ __device__ __forceinline__ float weight_f32(const F32Consts& c, float m1, float 
     const float G = (m1 <= c.g_hi) ? ex2f_(c.g_c * d * d) * c.g_pref : 0.f;
     p1 = ((1.f - c.lam) * Ppl + c.lam * G) * smoothing_f32(m1, c.dm, c.lo);
   }
-  // below ~1e-25 the term cannot matter next to any other sample, and the fp32 cdf would underflow
-  if (!(p1 > 1e-25f)) return 0.f;
+  // p1 == 0 (outside the support, or an fp32 underflow) must give weight 0 even when 1/cdf overflows (0 * inf)
+  if (!(p1 > 0.f)) return 0.f;
   if (!(c.lo <= m2 && m2 <= m1)) return 0.f;          // secondary support (tpl_notnorm(m2, beta, m_low, m1))
   float p2 = ex2f_(c.beta * lg2m2);
   if (c.mass_model != CHB_MASS_TPL) p2 *= smoothing_f32(m2, c.dm, c.lo);
@@ -171,7 +171,7 @@ __device__ __forceinline__ float weight_bf(const F32Consts& c, float m1, float m
   p2 = (p2 != p2) ? 0.f : p2;                          // 0/0 -> 0 (mass.py:340)
   const bool in2 = (c.lo <= m2) && (m2 <= m1);
   const float w = p1 * c.inv_norm_p1 * p2 * inv_prior;
-  return (in1 && in2 && p1 > 1e-25f) ? w : 0.f;
+  return (in1 && in2 && p1 > 0.f) ? w : 0.f;     // p1 == 0: never 0 * inf
 }
 // dL -> z with a fixed two-step scan (covers every bucket of a monotone table at 32 buckets/octave);
 // `more` tells the caller that a longer scan is needed (non-monotone / unusually dense tables).
@@ -240,3 +240,23 @@ __device__ __forceinline__ float zterm_inj_f32(const CosmoRateF32& c, float z, f
   const float dV = 12.566370614359172f * dHE * dCt * dCt;
   return dV * merger_rate_f32(c, z, lz) * rcpf_(opz) * rcpf_(fabsf(ddL) * opz * opz);
 }
+
+// z-grid terms of one (hyper-point, z): {dVc/dz, psi/(1+z) * trapezoid weight / (ddL/dz (1+z)^2)}
+// (cosmo.py:188-221,245-257, rate.py:96-129, likelihood.py:272,289).  E, ddL/dz, psi in fp32; the
+// comoving distance through the packed zi4 table.
+__device__ __forceinline__ float2 zgrid_terms_f32(const F32Consts& fc, const CosmoRateF32& cr, const double* __restrict__ P,
+                                                  const double* __restrict__ HC, int cm, double z, double tw) {
+  const float zf = (float)z, opz = 1.f + zf, lz = lg2f_(opz);
+  const double dCt = dCt_from_dCr(P, HC, HC[HC_DH] * (double)iinv_at_z_f32(fc, zf));
+  const float Ez = E_at_z_f32(cr, zf, opz, lz);
+  const float dHE = cr.dH * rcpf_(Ez);
+  float ddL = (float)dCt + dHE * opz;
+  if (cm == CHB_COSMO_MG_FLRW) {
+    const float Xi = cr.Xi0 + (1.f - cr.Xi0) * ex2f_(-cr.n * lz);
+    ddL = ddL * Xi + ((float)dCt * opz) * (cr.n * (cr.Xi0 - 1.f) * ex2f_(-(cr.n + 1.f) * lz));
+  }
+  const double dVv = 12.566370614359172 * (double)dHE * dCt * dCt;
+  const double ckv = (double)(merger_rate_f32(cr, zf, lz) * rcpf_(opz) * rcpf_(ddL * opz * opz)) * tw;
+  return make_float2((float)dVv, (float)ckv);
+}
+

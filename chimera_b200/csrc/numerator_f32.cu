@@ -30,9 +30,6 @@
 #ifndef CHB_K1_U
 #define CHB_K1_U 2           // samples in flight per thread in the reweighting loop (x2 with the prefetch)
 #endif
-#ifndef CHB_K3_MINB
-#define CHB_K3_MINB 6        // co-resident CTAs per SM of the 4-warp KDE variant (MODE 3, experimental)
-#endif
 #ifndef CHB_K2_MINB
 #define CHB_K2_MINB 3        // co-resident CTAs per SM of the KDE/z-integral kernel (MODE 2)
 #endif
@@ -40,8 +37,7 @@
 struct FPlan {
   int tab, zgrid, dV, ck, pgw, eg, dens, bc, bs, xwb, part, red, stage, total;
 };
-// mode 0: fused kernel; 1: reweighting only (table + reduction scratch); 2: KDE + z-integral on staged samples (no table);
-// 3: like 2, but the samples stay in global memory (no shared-memory stage; 4-warp CTAs, experimental)
+// mode 0: fused kernel; 1: reweighting only (table + reduction scratch); 2: KDE + z-integral on staged samples (no table)
 __host__ __device__ inline FPlan make_fplan(int tab_doubles, int Nz, int B, int Ns, int kind, int mode = 0, int nw = F_NW) {
   FPlan p;
   int o = 0;
@@ -64,16 +60,14 @@ __host__ __device__ inline FPlan make_fplan(int tab_doubles, int Nz, int B, int 
   p.part = o; o += (nw * Nz + 1) / 2;
   p.red = o; o += 64;
   o = (o + 1) & ~1;
-  p.stage = o; o += (mode == 3) ? 0 : (kind == CHB_PGW_FULL ? 3 : 1) * Ns;     // float2 {z,w} [+ float4 whitened]
+  p.stage = o; o += (kind == CHB_PGW_FULL ? 3 : 1) * Ns;     // float2 {z,w} [+ float4 whitened]
   p.total = o;
   return p;
 }
 static inline int f32_tab_doubles(const TableLayout& lay) { return lay.f32_total() - lay.f32_dl4(); }
 
-#define F3_NT 128            // threads per CTA of the MODE 3 variant
 size_t numerator_f32_smem_bytes(const NumArgs& a, int mode) {
-  return (size_t)make_fplan(f32_tab_doubles(a.mc.lay), a.Nz, a.binning ? a.num_bins : 0, a.Ns, a.kind, mode,
-                            mode == 3 ? F3_NT / 32 : F_NW).total * sizeof(double);
+  return (size_t)make_fplan(f32_tab_doubles(a.mc.lay), a.Nz, a.binning ? a.num_bins : 0, a.Ns, a.kind, mode, F_NW).total * sizeof(double);
 }
 
 __device__ __forceinline__ double nan_to_num_log_f(double like) {
@@ -143,25 +137,6 @@ __device__ __forceinline__ void kde_inplace(float2* xw, int n, const double* __r
   }
 }
 
-// z-grid terms of one (hyper-point, z): {dVc/dz, psi/(1+z) * trapezoid weight / (ddL/dz (1+z)^2)}
-// (cosmo.py:188-221,245-257, rate.py:96-129, likelihood.py:272,289).  E, ddL/dz, psi in fp32; the
-// comoving distance through the packed zi4 table.
-__device__ __forceinline__ float2 zgrid_terms_f32(const F32Consts& fc, const CosmoRateF32& cr, const double* __restrict__ P,
-                                                  const double* __restrict__ HC, int cm, double z, double tw) {
-  const float zf = (float)z, opz = 1.f + zf, lz = lg2f_(opz);
-  const double dCt = dCt_from_dCr(P, HC, HC[HC_DH] * (double)iinv_at_z_f32(fc, zf));
-  const float Ez = E_at_z_f32(cr, zf, opz, lz);
-  const float dHE = cr.dH * rcpf_(Ez);
-  float ddL = (float)dCt + dHE * opz;
-  if (cm == CHB_COSMO_MG_FLRW) {
-    const float Xi = cr.Xi0 + (1.f - cr.Xi0) * ex2f_(-cr.n * lz);
-    ddL = ddL * Xi + ((float)dCt * opz) * (cr.n * (cr.Xi0 - 1.f) * ex2f_(-(cr.n + 1.f) * lz));
-  }
-  const double dVv = 12.566370614359172 * (double)dHE * dCt * dCt;
-  const double ckv = (double)(merger_rate_f32(cr, zf, lz) * rcpf_(opz) * rcpf_(ddL * opz * opz)) * tw;
-  return make_float2((float)dVv, (float)ckv);
-}
-
 // One thread per (hyper-point, event, k): full-occupancy evaluation of the z-grid terms, so that the
 // persistent numerator CTAs only stream 8 B per grid point instead of running a latency-bound phase.
 __global__ void __launch_bounds__(256)
@@ -203,7 +178,7 @@ cudaError_t launch_zgrid_terms(const NumArgs& a, int h0, int nh, cudaStream_t s)
 // staged samples of a unit (one TMA bulk copy into shared memory).  Splitting lets either half run with three
 // co-resident CTAs per SM (no 42 KB table block next to the 40 KB sample stage) -- see DESIGN.md section 4.
 template <int KG, int MODE, int NT>
-__global__ void __launch_bounds__(NT, MODE == 0 ? 2 : (MODE == 1 ? CHB_K1_MINB : (MODE == 2 ? CHB_K2_MINB : CHB_K3_MINB)))
+__global__ void __launch_bounds__(NT, MODE == 0 ? 2 : (MODE == 1 ? CHB_K1_MINB : CHB_K2_MINB))
 numerator_f32_kernel(const NumArgs a) {
   constexpr int NW = NT / 32;
   extern __shared__ __align__(16) double sm[];
@@ -255,8 +230,8 @@ numerator_f32_kernel(const NumArgs a) {
     fence_proxy_async();
     __syncthreads();
     const double* tblk = a.tabs + (size_t)h * lay.total() + lay.off_f32();
-    float2* zw = (MODE == 1 || MODE == 3) ? a.zw_stage + (size_t)unit * Ns : zw_s;
-    if (tid == 0 && MODE != 3) {
+    float2* zw = (MODE == 1) ? a.zw_stage + (size_t)unit * Ns : zw_s;
+    if (tid == 0) {
       if (MODE != 2) {
         mbar_expect_tx(&bar, tab_bytes);
         bulk_g2s(tab, tblk + lay.f32_dl4(), tab_bytes, &bar);
@@ -304,10 +279,8 @@ numerator_f32_kernel(const NumArgs a) {
       s1 = u0.x; s2 = u0.y; zmn = u1.x; zmx = u1.y; zstd = __ldg(a.unit_stats + (size_t)unit * 8 + 4);
     }
     FPHASE(1);
-    if (MODE != 3) {
-      mbar_wait(&bar, phase);
-      phase ^= 1;
-    }
+    mbar_wait(&bar, phase);
+    phase ^= 1;
     FPHASE(0);
 
     const size_t so = (size_t)ev * Ns;
@@ -533,7 +506,7 @@ numerator_f32_kernel(const NumArgs a) {
         const WinPlan wp = sh_wp;
         float4* summ = reinterpret_cast<float4*>(pgw);
         int2* win = reinterpret_cast<int2*>(summ + 32);
-        kde1d_f32_win<NW, MODE == 3>(dxw, dn, G, eg[0], ustep, 0.5 * (eg[0] + eg[G - 1]), 0.8493218002880191 / bw, W, wp,
+        kde1d_f32_win<NW, false>(dxw, dn, G, eg[0], ustep, 0.5 * (eg[0] + eg[G - 1]), 0.8493218002880191 / bw, W, wp,
                             norm * 0.3989422804014327 / bw, summ, win, crs, reinterpret_cast<double*>(part), dens);
       } else {
         kde_inplace<NT>(dxw, dn, eg, G, bw, W, a.kernel, norm, part, NW * Nz, dens, ustep);
@@ -805,26 +778,17 @@ static inline int kind_group(int kind) { return kind == CHB_PGW_MARG ? 1 : (kind
   }
 cudaError_t numerator_f32_configure(int kind, int mode, size_t smem) {
   cudaError_t e = cudaSuccess;
-  if (mode == 3) return cudaFuncSetAttribute(numerator_f32_kernel<0, 3, F3_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   CHB_F32_DISPATCH(kind_group(kind), mode, e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   return e;
 }
 int numerator_f32_ctas_per_sm(int kind, int mode, size_t smem) {
   int n = 0;
   cudaError_t e = cudaSuccess;
-  if (mode == 3) {
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, numerator_f32_kernel<0, 3, F3_NT>, F3_NT, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
-    return n;
-  }
   CHB_F32_DISPATCH(kind_group(kind), mode, e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, F_NT, smem));
   if (e != cudaSuccess) { cudaGetLastError(); return 0; }
   return n;
 }
 cudaError_t launch_numerator_f32(const NumArgs& a, int mode, int grid, size_t smem, cudaStream_t s) {
-  if (mode == 3) {                              // 4-warp KDE variant: kind group 0 only
-    numerator_f32_kernel<0, 3, F3_NT><<<grid, F3_NT, smem, s>>>(a);
-    return cudaGetLastError();
-  }
   CHB_F32_DISPATCH(kind_group(a.kind), mode, (kern<<<grid, F_NT, smem, s>>>(a)));
   return cudaGetLastError();
 }

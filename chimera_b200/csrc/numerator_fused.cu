@@ -1,0 +1,590 @@
+// numerator_fused.cu -- ONE kernel per step for the 1-D kinds of the fp32 mode (non-pixelated and 'approximate'):
+// population reweighting -> statistics -> [binning] -> KDE -> interpolation -> z-integral -> log, per (event, hyper-point)
+// unit, with the reweighted samples living only in shared memory (likelihood.py:105-154, 266-301; pop_wrapper.py:67-80;
+// utils/math.py:32-89).
+//
+// Why it replaces the split MODE 1 -> stage buffer -> MODE 2 pair of numerator_f32.cu (round 1):
+//   * no stage buffer: the split form wrote and re-read 8 B per (sample, hyper-point) through HBM (2 x 10.2 GB per C3 step);
+//   * no 42 KB table block next to the 40 KB sample stage.  The packed tables (dl4 | cd4 | lut, models.cuh) are read
+//     with ld.global.nc through L1: the samples of an event are sorted by dL at upload, so a warp's 64 consecutive
+//     samples fall into one or two rows of dl4, and an event's source-frame masses into a few dozen rows of cd4 -- the
+//     working set per CTA is a few KB.  53 KB of shared memory per CTA -> 3-4 co-resident CTAs per SM;
+//   * no rescaling pass: the stage keeps {z - z0, log2 w} pairs, the scale 1/bw rides in the FFMA2 that forms x' - g
+//     (kde_win.cuh, RAW), 1/sum(w) in the exponent offset; the per-chunk summaries the windows need are taken while the
+//     samples are still in registers (one redux per 64 samples);
+//   * bandwidth and tiling are derived by every thread from the block-reduced statistics (no one-thread section and
+//     no barrier behind it); the per-hyper-point single-precision constants come from the FC row build_tables_kernel
+//     wrote (no fp64 divisions per thread per unit);
+//   * binning (utils/math.py:32-46) runs on the shared-memory stage by contiguous runs of the sorted samples.
+// fp64 is kept for: tables, block-level statistics, bandwidth, grid geometry, cross-warp accumulation, interpolation,
+// z-integral and the final reduction -- as in numerator_f32.cu.
+#include "common.cuh"
+#include "models_f32.cuh"
+#include "kde_f32.cuh"
+#include "kde_win.cuh"
+#include <algorithm>
+
+#ifndef FU_NT
+#define FU_NT 256
+#endif
+#define FU_NW (FU_NT / 32)
+#define FU_SUB 64                 // samples per warp iteration of the reweighting loop = granularity of the chunk summaries
+#ifndef CHB_FU_MINB
+#define CHB_FU_MINB 3             // co-resident CTAs per SM the kernel is compiled for
+#endif
+
+struct FusedPlan {                // byte offsets into dynamic shared memory
+  int stage, rows, dens, bc, bs, bx, sub, summ, win, cr, red, total;
+};
+__host__ __device__ inline FusedPlan make_fused_plan(int Ns, int Nz, int B) {
+  FusedPlan p;
+  const int G = Nz / 2;
+  const int Bp = (B + 1) & ~1;
+  int o = 0;
+  p.stage = o; o += Ns * 8;                       // float4 per two samples {dz_a, dz_b, v_a, v_b}
+  p.rows = o; o += FU_NW * G * 8;                 // per-warp partial rows (doubles)
+  p.dens = o; o += ((G + 1) & ~1) * 8;
+  p.bc = o; o += Bp * 8;
+  p.bs = o; o += Bp * 8;
+  p.bx = o; o += Bp * 8;                          // binned data set in pair layout
+  p.sub = o; o += ((Ns + FU_SUB - 1) / FU_SUB) * 16;
+  p.summ = o; o += 32 * 16;
+  p.win = o; o += 32 * 8;
+  p.cr = o; o += 16 * 4;
+  p.red = o; o += 64 * 8;
+  p.total = o;
+  return p;
+}
+size_t numerator_fused_smem_bytes(const NumArgs& a) {
+  return (size_t)make_fused_plan(a.Ns, a.Nz, a.binning ? a.num_bins : 0).total;
+}
+bool numerator_fused_supported(const NumArgs& a) {
+  return a.fp_mode == CHB_FP32 && (a.kind == CHB_PGW_1D || a.kind == CHB_PGW_APPROX) && a.use_cut && (a.Ns % 2 == 0) &&
+         a.Nz / 2 >= 2 && a.s4 != nullptr;
+}
+
+__device__ __forceinline__ double nan_to_num_log_fu(double like) {
+  double l = log(like);                  // likelihood.py:296-297
+  if (isnan(l)) return -INFINITY;
+  if (isinf(l)) return l > 0 ? CHB_DBL_MAX : -CHB_DBL_MAX;
+  return l;
+}
+
+struct FuStats { double a, b, c, d; float mn, mx; };
+__device__ __forceinline__ FuStats fu_block_stats(FuStats v, double* red /* >= 6*FU_NW doubles */) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    v.a += __shfl_xor_sync(0xffffffffu, v.a, o);
+    v.b += __shfl_xor_sync(0xffffffffu, v.b, o);
+    v.c += __shfl_xor_sync(0xffffffffu, v.c, o);
+    v.d += __shfl_xor_sync(0xffffffffu, v.d, o);
+  }
+  v.mn = warp_min_f32(v.mn); v.mx = warp_max_f32(v.mx);
+  if (lane == 0) {
+    red[w * 6 + 0] = v.a; red[w * 6 + 1] = v.b; red[w * 6 + 2] = v.c; red[w * 6 + 3] = v.d;
+    red[w * 6 + 4] = (double)v.mn; red[w * 6 + 5] = (double)v.mx;
+  }
+  __syncthreads();
+  FuStats r = {0.0, 0.0, 0.0, 0.0, INFINITY, -INFINITY};
+#pragma unroll
+  for (int i = 0; i < FU_NW; ++i) {
+    r.a += red[i * 6 + 0]; r.b += red[i * 6 + 1]; r.c += red[i * 6 + 2]; r.d += red[i * 6 + 3];
+    r.mn = fminf(r.mn, (float)red[i * 6 + 4]); r.mx = fmaxf(r.mx, (float)red[i * 6 + 5]);
+  }
+  return r;
+}
+
+// ---- population reweighting in single precision (pop_wrapper.py:67-80) ---------------------------------------
+// per-hyper-point view of the packed tables (global memory, read through L1) and the FC constants
+struct FuTab {
+  const float4* __restrict__ dl4; const float4* __restrict__ cd4; const unsigned short* __restrict__ lut;
+  int rc, rm, nb, b0;
+  float z_top, lg2_m0, inv_lg2_mstep, lo, hi, dm, neg_alpha, beta, kA, kG, mu, g_hi, g_c, mb, neg_alpha2, cdl_x, cdl_y;
+};
+__device__ __forceinline__ FuTab make_fu_tab(const TableLayout& lay, const double* __restrict__ f32blk, const float* __restrict__ FC) {
+  FuTab t;
+  t.dl4 = reinterpret_cast<const float4*>(f32blk + lay.f32_dl4());
+  t.cd4 = reinterpret_cast<const float4*>(f32blk + lay.f32_cd4());
+  t.lut = reinterpret_cast<const unsigned short*>(f32blk + lay.f32_lut());
+  t.rc = lay.rc; t.rm = lay.rm;
+  t.b0 = __float_as_int(FC[FC_LUT_B0]); t.nb = __float_as_int(FC[FC_LUT_NB]);
+  t.z_top = FC[FC_Z_TOP]; t.lg2_m0 = FC[FC_LG2_M0]; t.inv_lg2_mstep = FC[FC_INV_LG2_MSTEP];
+  t.lo = FC[FC_LO]; t.hi = FC[FC_HI]; t.dm = FC[FC_DM]; t.neg_alpha = FC[FC_NEG_ALPHA]; t.beta = FC[FC_BETA];
+  t.kA = FC[FC_KA]; t.kG = FC[FC_KG]; t.mu = FC[FC_MU]; t.g_hi = FC[FC_G_HI]; t.g_c = FC[FC_G_C];
+  t.mb = FC[FC_MB]; t.neg_alpha2 = FC[FC_NEG_ALPHA2]; t.cdl_x = FC[FC_CDL_X]; t.cdl_y = FC[FC_CDL_Y];
+  return t;
+}
+
+// z_from_dGW (cosmo.py:260-264): float-bits LUT -> candidate row, two-step scan (every bucket of a monotone table
+// at 32 buckets per octave), rare longer scans in a loop; clamped ends like numpy.interp.
+__device__ __forceinline__ float fu_z_from_dL(const FuTab& t, float dL) {
+  int b = (int)(__float_as_uint(dL) >> CHB_LUT_SHIFT) - t.b0;
+  b = max(0, min(b, t.nb - 1));
+  int k = __ldg(t.lut + b);
+  float4 e = __ldg(t.dl4 + k);
+  if (dL >= e.w && k < t.rc - 2) { ++k; e = __ldg(t.dl4 + k); }
+  if (dL >= e.w && k < t.rc - 2) { ++k; e = __ldg(t.dl4 + k); }
+  while (dL >= e.w && k < t.rc - 2) { ++k; e = __ldg(t.dl4 + k); }
+  float z = fmaf(dL - e.x, e.z, e.y);
+  z = (dL >= e.w) ? t.z_top : z;
+  return (dL <= 0.f) ? 0.f : z;
+}
+
+// mass.py:255-264 with one reciprocal: dm/x + dm/(x-dm) = dm (2x - dm) / (x (x - dm))
+__device__ __forceinline__ float fu_smoothing(float m, float dm, float lo) {
+  const float x = m - lo;
+  const float tt = dm * (2.f * x - dm) * rcpf_(x * (x - dm));
+  float S = rcpf_(1.f + ex2f_(tt * CHB_LOG2E_F));
+  S = (x > dm) ? 1.f : S;
+  return (x < 0.f) ? 0.f : S;
+}
+
+// p_m1m2 / pe_prior (mass.py:334-345, pop_wrapper.py:79); lm1/lm2 = log2 of the source-frame masses.
+// SMOOTH = false: the caller has checked that every mass of the warp is above m_low + delta_m (taper == 1 exactly).
+template <int MASS, bool SMOOTH>
+__device__ __forceinline__ float fu_weight(const FuTab& t, float m1, float m2, float lm1, float lm2, float inv_prior) {
+  float p1;                                                  // primary pdf, already divided by norm_p_m1
+  if (MASS == CHB_MASS_TPL) {
+    p1 = ex2f_(fmaf(t.neg_alpha, lm1, t.kA));
+  } else if (MASS == CHB_MASS_BPL) {
+    const float pa = ex2f_(fmaf(t.neg_alpha, lm1, t.kA)), pb = ex2f_(fmaf(t.neg_alpha2, lm1, t.kG));
+    p1 = ((m1 <= t.mb) ? pa : 0.f) + ((m1 >= t.mb) ? pb : 0.f);
+  } else {
+    const float d = m1 - t.mu;
+    const float g = ex2f_(fmaf(t.g_c * d, d, t.kG));
+    p1 = ex2f_(fmaf(t.neg_alpha, lm1, t.kA)) + ((m1 <= t.g_hi) ? g : 0.f);
+  }
+  float p2 = ex2f_(t.beta * lm2);
+  if (SMOOTH && MASS != CHB_MASS_TPL) { p1 *= fu_smoothing(m1, t.dm, t.lo); p2 *= fu_smoothing(m2, t.dm, t.lo); }
+  int i = (int)((lm1 - t.lg2_m0) * t.inv_lg2_mstep);
+  i = max(0, min(i, t.rm - 2));
+  // (an index that is one off at a knot extrapolates the neighbouring segment by an ulp: same value to rounding)
+  const float4 e = __ldg(t.cd4 + i);
+  float cdf = fmaf(m1 - e.x, e.z, e.y);
+  cdf = (m1 >= t.cdl_x) ? t.cdl_y : cdf;
+  p2 = p2 * rcpf_(cdf);
+  p2 = (p2 != p2) ? 0.f : p2;                                // 0/0 -> 0 (mass.py:340)
+  const bool in = (t.lo <= m1) && (m1 <= t.hi) && (t.lo <= m2) && (m2 <= m1) && (p1 > 0.f);   // p1 == 0: never 0 * inf
+  return in ? p1 * p2 * inv_prior : 0.f;
+}
+
+// One pass over the event's packed samples: {z - z0, v} pairs to the shared-memory stage (v = log2 w when `want_lw`,
+// else w), per-warp statistics {sum w, sum w^2, sum dz, sum dz^2, min dz, max dz} to red[warp*6..] (+ z0 in red[63]), and
+// per 64-sample block {min dz, max dz, max log2 w, dz of that sample} over the samples with w > 0.  Static round-robin
+// of blocks over the warps: bit-reproducible.  NOT inlined: the loop gets the kernel's whole register budget to itself
+// (the unit-level state of the caller is saved around the call once per unit instead of spilling inside the loop).
+template <int MASS>
+__device__ __noinline__ void fu_reweight(const double* __restrict__ f32blk, int rc, int rcs, int rms, int rm,
+                                         const float* __restrict__ FC, const float4* __restrict__ s4,
+                                         const float2* __restrict__ l2, int Ns, int want_lw_i, float4* __restrict__ stage,
+                                         float4* __restrict__ sub, double* __restrict__ red) {
+  TableLayout lay; lay.rc = rc; lay.rm = rm; lay.rcs = rcs; lay.rms = rms;
+  const FuTab t = make_fu_tab(lay, f32blk, FC);
+  const bool want_lw = want_lw_i != 0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // z shifted by the redshift of the event's median-dL sample: {z - z0} is exact in fp32 and small, so the one-pass
+  // variance does not cancel and the scaled coordinates of the pair sums keep ~1e-6 absolute accuracy
+  const float z0 = fu_z_from_dL(t, __ldg(&s4[Ns / 2].x));
+  float fa = 0.f, fb = 0.f, fcs = 0.f, fd = 0.f, mn = INFINITY, mx = -INFINITY;
+  int cb = warp * FU_SUB;
+  float4 sa, sb, ll, nsa, nsb, nll;
+  if (cb < Ns) {
+    const int j = min(cb + 2 * lane, Ns - 2);                  // tail lanes recompute the last pair, never stored
+    sa = __ldg(s4 + j); sb = __ldg(s4 + j + 1); ll = __ldg(reinterpret_cast<const float4*>(l2 + j));
+  }
+  while (cb < Ns) {
+    const int nbase = cb + FU_NW * FU_SUB;
+    if (nbase < Ns) {                                          // request the next block before evaluating this one
+      const int j = min(nbase + 2 * lane, Ns - 2);
+      nsa = __ldg(s4 + j); nsb = __ldg(s4 + j + 1); nll = __ldg(reinterpret_cast<const float4*>(l2 + j));
+    }
+    const bool valid = cb + 2 * lane < Ns;
+    const float za = fu_z_from_dL(t, sa.x), zb = fu_z_from_dL(t, sb.x);
+    const float opa = 1.f + za, opb = 1.f + zb;
+    const float ra = rcpf_(opa), rb = rcpf_(opb), lza = lg2f_(opa), lzb = lg2f_(opb);
+    const float m1a = sa.y * ra, m2a = sa.z * ra, m1b = sb.y * rb, m2b = sb.z * rb;
+    float wa, wb;
+    const bool taper = (MASS != CHB_MASS_TPL) &&
+                       (!(m2a - t.lo > t.dm) || !(m1a - t.lo > t.dm) || !(m2b - t.lo > t.dm) || !(m1b - t.lo > t.dm));
+    if (MASS != CHB_MASS_TPL && __any_sync(0xffffffffu, taper)) {
+      wa = fu_weight<MASS, true>(t, m1a, m2a, ll.x - lza, ll.y - lza, sa.w);
+      wb = fu_weight<MASS, true>(t, m1b, m2b, ll.z - lzb, ll.w - lzb, sb.w);
+    } else {
+      wa = fu_weight<MASS, false>(t, m1a, m2a, ll.x - lza, ll.y - lza, sa.w);
+      wb = fu_weight<MASS, false>(t, m1b, m2b, ll.z - lzb, ll.w - lzb, sb.w);
+    }
+    const float dza = za - z0, dzb = zb - z0;
+    if (valid) {
+      fa += wa + wb; fb = fmaf(wa, wa, fmaf(wb, wb, fb)); fcs += dza + dzb; fd = fmaf(dza, dza, fmaf(dzb, dzb, fd));
+      mn = fminf(mn, fminf(dza, dzb)); mx = fmaxf(mx, fmaxf(dza, dzb));
+    }
+    if (want_lw) {
+      const bool pa = valid && wa > 0.f, pb = valid && wb > 0.f;          // zero / NaN weights add exactly 0
+      const float lwa = pa ? lg2f_(wa) : -INFINITY, lwb = pb ? lg2f_(wb) : -INFINITY;
+      if (valid) stage[(cb >> 1) + lane] = make_float4(dza, dzb, lwa, lwb);
+      const float lo = warp_min_f32(fminf(pa ? dza : INFINITY, pb ? dzb : INFINITY));
+      const float hi = warp_max_f32(fmaxf(pa ? dza : -INFINITY, pb ? dzb : -INFINITY));
+      const float lm = fmaxf(lwa, lwb), xm = (lwa >= lwb) ? dza : dzb;
+      const float lmw = warp_max_f32(lm);
+      const unsigned pick = __ballot_sync(0xffffffffu, lm == lmw && lm > -INFINITY);
+      const float xmw = __shfl_sync(0xffffffffu, xm, pick ? (__ffs(pick) - 1) : 0);
+      if (lane == 0) sub[cb / FU_SUB] = make_float4(lo, hi, pick ? lmw : -INFINITY, xmw);
+    } else if (valid) {
+      stage[(cb >> 1) + lane] = make_float4(dza, dzb, wa, wb);
+    }
+    cb = nbase;
+    sa = nsa; sb = nsb; ll = nll;
+  }
+  // warp-level reduction; fp64 from here on
+  double da = (double)fa, db = (double)fb, dc = (double)fcs, dd = (double)fd;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    da += __shfl_xor_sync(0xffffffffu, da, o);
+    db += __shfl_xor_sync(0xffffffffu, db, o);
+    dc += __shfl_xor_sync(0xffffffffu, dc, o);
+    dd += __shfl_xor_sync(0xffffffffu, dd, o);
+  }
+  mn = warp_min_f32(mn); mx = warp_max_f32(mx);
+  if (lane == 0) {
+    red[warp * 6 + 0] = da; red[warp * 6 + 1] = db; red[warp * 6 + 2] = dc; red[warp * 6 + 3] = dd;
+    red[warp * 6 + 4] = (double)mn; red[warp * 6 + 5] = (double)mx;
+    if (warp == 0) red[63] = (double)z0;
+  }
+}
+
+// Direct pair sums for data sets without a window plan (few samples, coarse grids, the 200 bins of the reference's
+// default options, Epanechnikov).  pairs[i] = {x_a, x_b, v_a, v_b}; x' = x * sf; grid point g sits at gfirst + g hd
+// (scaled units); Gaussian: v = log2 w', term 2^(v + koff - d^2); Epanechnikov: v = w, term v max(1 - d^2, 0).
+// Lane owns R grid points of a 32R-point pass; the warps split the pairs; rows[warp][g] (doubles) receive the sums.
+template <int R, bool GAUSS>
+__device__ __forceinline__ void fu_direct_pass(const float4* __restrict__ pairs, int npairs, int G, int g_base, double gfirst,
+                                               double hd, float sf, float koff, double* __restrict__ rows) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float gp[R], acc[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int g = g_base + r * 32 + lane;
+    gp[r] = (g < G) ? (float)(gfirst + (double)g * hd) : 3.0e18f;
+    acc[r] = 0.f;
+  }
+  const int per = (npairs + FU_NW - 1) / FU_NW;
+  const int j0 = min(npairs, warp * per), j1 = min(npairs, j0 + per);
+#pragma unroll 2
+  for (int j = j0; j < j1; ++j) {
+    const float4 v = pairs[j];
+    const float xa = v.x * sf, xb = v.y * sf;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const float da = gp[r] - xa, db = gp[r] - xb;
+      if (GAUSS) {
+        acc[r] += ex2_ftz(fmaf(-da, da, v.z + koff)) + ex2_ftz(fmaf(-db, db, v.w + koff));
+      } else {
+        acc[r] = fmaf(v.z, fmaxf(fmaf(-da, da, 1.f), 0.f), acc[r]);
+        acc[r] = fmaf(v.w, fmaxf(fmaf(-db, db, 1.f), 0.f), acc[r]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int g = g_base + r * 32 + lane;
+    if (g < G) rows[warp * G + g] = (double)acc[r];
+  }
+}
+// dens[g] = scale * sum over the data set; whole-CTA call; ends with dens[] written (no barrier after)
+__device__ __noinline__ void fu_direct(const float4* __restrict__ pairs, int npairs, int G, double gfirst, double hd,
+                                          float sf, float koff, bool gauss, double scale, double* __restrict__ rows,
+                                          double* __restrict__ dens) {
+  if (G <= 160) {
+    if (gauss) fu_direct_pass<5, true>(pairs, npairs, G, 0, gfirst, hd, sf, koff, rows);
+    else fu_direct_pass<5, false>(pairs, npairs, G, 0, gfirst, hd, sf, koff, rows);
+  } else {
+    for (int gb = 0; gb < G; gb += 256) {
+      if (gauss) fu_direct_pass<8, true>(pairs, npairs, G, gb, gfirst, hd, sf, koff, rows);
+      else fu_direct_pass<8, false>(pairs, npairs, G, gb, gfirst, hd, sf, koff, rows);
+    }
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < G; g += FU_NT) {
+    double acc = 0.0;
+#pragma unroll
+    for (int w = 0; w < FU_NW; ++w) acc += rows[w * G + g];
+    dens[g] = acc * scale;
+  }
+}
+
+// Windowed recurrence KDE of the staged samples (kde_win.cuh) -- NOT inlined, for the same reason as fu_reweight.
+// Merges the 64-sample block summaries into the plan's chunks (scaled units, weights normalised), then phases B and C.
+__device__ __noinline__ void fu_kde_win(const float4* __restrict__ stage, int Ns, int G, double gfirst, double hd, int R,
+                                        int LPS, int chunk, int nchunks, double scale, float sf, float koff,
+                                        const float4* __restrict__ sub, float4* __restrict__ summ, int2* __restrict__ win,
+                                        float* __restrict__ cr, double* __restrict__ rows, double* __restrict__ dens) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  WinPlan wp; wp.R = R; wp.LPS = LPS; wp.chunk = chunk; wp.nchunks = nchunks;
+  const float h = (float)hd;
+  if (tid < 16) cr[tid] = exp2f(-(h * h) * (float)(tid * (tid - 1)));
+  if (warp == 1 && lane < nchunks) {
+    float lo = INFINITY, hi = -INFINITY, lm = -INFINITY, xm = 0.f;
+    const int nsub = chunk / FU_SUB, b0 = lane * nsub, b1 = min(b0 + nsub, (Ns + FU_SUB - 1) / FU_SUB);
+    for (int i = b0; i < b1; ++i) {
+      const float4 v = sub[i];
+      lo = fminf(lo, v.x); hi = fmaxf(hi, v.y);
+      if (v.z > lm) { lm = v.z; xm = v.w; }
+    }
+    summ[lane] = make_float4(lo * sf, hi * sf, lm + koff, xm * sf);
+    win[lane] = make_int2(G, -1);
+  }
+  __syncthreads();
+  kde_win_BC<FU_NW, false, true>(reinterpret_cast<const float2*>(stage), Ns, G, gfirst, hd, wp, scale, summ, win, cr, rows,
+                                 dens, sf, koff);
+}
+
+__global__ void __launch_bounds__(FU_NT, CHB_FU_MINB)
+numerator_fused_kernel(const NumArgs a) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  __shared__ double P[CHB_NPAR];
+  __shared__ double HC[CHB_NHC];
+  __shared__ float FC[CHB_NFC];
+
+  const TableLayout lay = a.mc.lay;
+  const int Ns = a.Ns, Nz = a.Nz, Pp = a.P, B = a.binning ? a.num_bins : 0, G = Nz / 2;
+  const FusedPlan pl = make_fused_plan(Ns, Nz, B);
+  float4* stage = reinterpret_cast<float4*>(smraw + pl.stage);
+  double* rows = reinterpret_cast<double*>(smraw + pl.rows);
+  double* dens = reinterpret_cast<double*>(smraw + pl.dens);
+  double* bc = reinterpret_cast<double*>(smraw + pl.bc);
+  double* bs = reinterpret_cast<double*>(smraw + pl.bs);
+  float4* bx = reinterpret_cast<float4*>(smraw + pl.bx);
+  float4* sub = reinterpret_cast<float4*>(smraw + pl.sub);
+  float4* summ = reinterpret_cast<float4*>(smraw + pl.summ);
+  int2* win = reinterpret_cast<int2*>(smraw + pl.win);
+  float* cr = reinterpret_cast<float*>(smraw + pl.cr);
+  double* red = reinterpret_cast<double*>(smraw + pl.red);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool pixelated = (a.kind != CHB_PGW_1D);
+  const bool has_cat = (a.mc.catalog_kind == 1);
+  const bool gauss = (a.kernel == CHB_KERNEL_GAUSS);
+  const bool want_lw = gauss && !a.binning;                  // the stage carries log2 w for the Gaussian pair sums
+
+  const long long units = (long long)a.Nev * a.n_hyper;
+  for (long long unit = blockIdx.x; unit < units; unit += gridDim.x) {
+    const int ev = (int)(unit / a.n_hyper), h = (int)(unit % a.n_hyper);
+    const double* tblk = a.tabs + (size_t)h * lay.total() + lay.off_f32();
+    __syncthreads();                                         // the previous unit is done with every shared array
+    if (tid < CHB_NPAR) P[tid] = a.hyper[(size_t)h * CHB_NPAR + tid];
+    else if (tid >= 64 && tid < 64 + CHB_NHC) HC[tid - 64] = a.HC[(size_t)h * CHB_NHC + tid - 64];
+    else if (tid >= 128 && tid < 128 + CHB_NFC) FC[tid - 128] = __ldg(reinterpret_cast<const float*>(tblk + lay.f32_fc()) + tid - 128);
+    for (int i = tid; i < FU_NW * G; i += FU_NT) rows[i] = 0.0;
+    __syncthreads();
+
+    // ---- stage 1: reweighting ---------------------------------------------------------------
+    {
+      const size_t so = (size_t)ev * Ns;
+      switch (a.mc.mass_model) {
+        case CHB_MASS_TPL: fu_reweight<CHB_MASS_TPL>(tblk, lay.rc, lay.rcs, lay.rms, lay.rm, FC, a.s4 + so, a.l2 + so, Ns, want_lw, stage, sub, red); break;
+        case CHB_MASS_BPL: fu_reweight<CHB_MASS_BPL>(tblk, lay.rc, lay.rcs, lay.rms, lay.rm, FC, a.s4 + so, a.l2 + so, Ns, want_lw, stage, sub, red); break;
+        default: fu_reweight<CHB_MASS_PLP>(tblk, lay.rc, lay.rcs, lay.rms, lay.rm, FC, a.s4 + so, a.l2 + so, Ns, want_lw, stage, sub, red); break;
+      }
+    }
+    __syncthreads();                                         // publishes stage[], sub[] and the warp partials
+    FuStats st = {0.0, 0.0, 0.0, 0.0, INFINITY, -INFINITY};
+#pragma unroll
+    for (int i = 0; i < FU_NW; ++i) {
+      st.a += red[i * 6 + 0]; st.b += red[i * 6 + 1]; st.c += red[i * 6 + 2]; st.d += red[i * 6 + 3];
+      st.mn = fminf(st.mn, (float)red[i * 6 + 4]); st.mx = fmaxf(st.mx, (float)red[i * 6 + 5]);
+    }
+    const float z0 = (float)red[63];
+    const double s1 = st.a, s2 = st.b;
+    const double zmn = (double)z0 + (double)st.mn, zmx = (double)z0 + (double)st.mx;
+    const double dzmean = st.c / Ns;
+    const double zstd = sqrt(fmax(st.d / Ns - dzmean * dzmean, 0.0));    // one-pass variance about z0
+    const double norm = s1 / Ns;                  // likelihood.py:111
+    const double neff = s1 * s1 / s2;             // likelihood.py:112
+    const bool ok = (neff >= a.pe_neff);
+
+    double* pout = nullptr;
+    if (a.p_gw_out) pout = a.p_gw_out + ((size_t)h * a.Nev + ev) * (size_t)(pixelated ? Pp : 1) * Nz;
+    const int npix = pixelated ? a.neff_pix[ev] : 1;
+    if (!ok) {
+      if (pout) for (int i = tid; i < (pixelated ? Pp : 1) * Nz; i += FU_NT) pout[i] = 0.0;
+      if (tid == 0) { a.log_like[(size_t)h * a.Nev + ev] = nan_to_num_log_fu(0.0); a.like_raw[(size_t)h * a.Nev + ev] = 0.0; }
+      continue;
+    }
+
+    // ---- effective grid (likelihood.py:115-123): linspace(lb, ub, G), never materialised ---------------
+    const double lb = (zmn - a.cut_grid * zstd > 0.0) ? zmn - a.cut_grid * zstd : 1.e-8;
+    const double ub = zmx + a.cut_grid * zstd;
+    const double step = (ub - lb) / (double)(G - 1);
+    auto eg_at = [&](int i) -> double { return (i == G - 1) ? ub : __dadd_rn(__dmul_rn((double)i, step), lb); };
+
+    if (!a.binning) {
+      // ---- bandwidth (utils/math.py:62-70), every thread the same value ----------------------------
+      const double neff_k = 1.0 / (s2 / (s1 * s1));
+      double bw;
+      if (a.bw_method == CHB_BW_SCOTT) bw = (double)ex2f_(-0.2f * lg2f_((float)neff_k)) * zstd;
+      else if (a.bw_method == CHB_BW_SILVERMAN) bw = (double)ex2f_(-0.2f * lg2f_((float)(neff_k * 3.0 / 4.0))) * zstd;
+      else bw = a.bw_value * zstd;
+      const double s = gauss ? 0.8493218002880191 / bw : 1.0 / bw;       // sqrt(log2(e)/2) / bw
+      const float sf = (float)s;
+      const double gfirst = (lb - (double)z0) * (double)sf, hd = step * (double)sf;
+      const double scale = norm * (gauss ? 0.3989422804014327 : 0.75) / bw;
+      WinPlan wp;
+      const bool windowed = gauss && a.kde_win_iters > 0 && Nz >= 64 &&
+                            win_plan(G, Ns, (float)hd, a.kde_win_iters, 32, wp, FU_SUB);
+      if (windowed) {
+        fu_kde_win(stage, Ns, G, gfirst, hd, wp.R, wp.LPS, wp.chunk, wp.nchunks, scale, sf, -lg2f_((float)s1), sub, summ, win,
+                   cr, rows, dens);
+      } else {
+        const float koff = gauss ? -lg2f_((float)s1) : 0.f;
+        fu_direct(stage, Ns / 2, G, gfirst, hd, sf, koff, gauss, gauss ? scale : scale / s1, rows, dens);
+      }
+    } else {
+      // ---- binning1d (utils/math.py:32-46) on the shared-memory stage, then the KDE of the B bin centres -------
+      const double bstep = (zmx - zmn) / (double)B;
+      for (int i = tid; i < B; i += FU_NT) {
+        const double e0 = __dadd_rn(__dmul_rn((double)i, bstep), zmn);
+        const double e1 = (i + 1 == B) ? zmx : __dadd_rn(__dmul_rn((double)(i + 1), bstep), zmn);
+        bc[i] = (e0 + e1) / 2;
+        bs[i] = 0.0;
+      }
+      __syncthreads();
+      {
+        // the samples are sorted by dL, hence by z: a bin is a contiguous run.  Every thread walks a contiguous block
+        // of pairs, sums each run in a register and touches shared memory once per run.  Correct for any order.
+        const int npairs = Ns / 2;
+        const int per = (npairs + FU_NT - 1) / FU_NT;
+        const int ja = min(npairs, tid * per), jb = min(npairs, ja + per);
+        const double invB = (double)B / (zmx - zmn), off = (double)z0 - zmn;
+        int cur = -1;
+        double run = 0.0;
+        for (int j = ja; j < jb; ++j) {
+          const float4 v = stage[j];
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const double f = floor(((double)(q ? v.y : v.x) + off) * invB);
+            if (isnan(f)) continue;
+            const int b = (int)fmin(fmax(f, 0.0), (double)(B - 1));
+            if (b != cur) {
+              if (cur >= 0) atomicAdd(&bs[cur], run);
+              cur = b; run = 0.0;
+            }
+            run += (double)(q ? v.w : v.z);
+          }
+        }
+        if (cur >= 0) atomicAdd(&bs[cur], run);
+      }
+      __syncthreads();
+      FuStats u = {0.0, 0.0, 0.0, 0.0, 0.f, 0.f};
+      for (int i = tid; i < B; i += FU_NT) { u.a += bs[i]; u.b += bs[i] * bs[i]; u.c += bc[i]; u.d += bc[i] * bc[i]; }
+      __syncthreads();                                       // `red` was read by every thread after the first reduction
+      u = fu_block_stats(u, red);
+      const double W = u.a, Q = u.b;
+      const double cmean = u.c / B;
+      const double dstd = sqrt(fmax(u.d / B - cmean * cmean, 0.0));   // std of the BIN CENTRES (math.py:67 on binning1d's output)
+      const double neff_k = 1.0 / (Q / (W * W));
+      double bw;
+      if (a.bw_method == CHB_BW_SCOTT) bw = pow(neff_k, -0.2) * dstd;
+      else if (a.bw_method == CHB_BW_SILVERMAN) bw = pow(neff_k * 3.0 / 4.0, -0.2) * dstd;
+      else bw = a.bw_value * dstd;
+      const double s = gauss ? 0.8493218002880191 / bw : 1.0 / bw;
+      const double c = 0.5 * (lb + ub);
+      // pair layout of the binned data set: {x'_a, x'_b, v_a, v_b}, x' = (centre - c) s, v = log2(w/W) | w/W
+      const int Bp = (B + 1) / 2;
+      for (int i = tid; i < Bp; i += FU_NT) {
+        const int ia = 2 * i, ib = 2 * i + 1;
+        const float xa = (float)((bc[ia] - c) * s), xb = (ib < B) ? (float)((bc[ib] - c) * s) : 0.f;
+        const float wa = (float)(bs[ia] / W), wb = (ib < B) ? (float)(bs[ib] / W) : 0.f;
+        bx[i] = gauss ? make_float4(xa, xb, wa > 0.f ? lg2f_(wa) : -INFINITY, wb > 0.f ? lg2f_(wb) : -INFINITY)
+                      : make_float4(xa, xb, wa, wb);
+      }
+      __syncthreads();
+      fu_direct(bx, Bp, G, (lb - c) * s, step * s, 1.f, 0.f, gauss, norm * (gauss ? 0.3989422804014327 : 0.75) / bw, rows, dens);
+    }
+    __syncthreads();
+
+    // ---- p_gw on the event grid (likelihood.py:139-141) fused with the integrand (likelihood.py:266-292) --------
+    const double* zgr = a.zgrids + (size_t)ev * Nz;
+    const double inv_step = 1.0 / step;
+    auto pgw_at = [&](double x) -> double {
+      if (x < lb || x > ub) return 0.0;
+      int i = (int)((x - lb) * inv_step);
+      i = max(0, min(i, G - 2));
+      while (i < G - 2 && x >= eg_at(i + 1)) ++i;
+      while (i > 0 && x < eg_at(i)) --i;
+      const double x0 = eg_at(i), dx = eg_at(i + 1) - x0, f0 = dens[i], df = dens[i + 1] - f0;
+      return (fabs(dx) <= 4.930380657631324e-32) ? f0 : f0 + ((x - x0) / dx) * df;
+    };
+    const float2* zt = a.zterms ? a.zterms + ((size_t)(h - a.zterms_h0) * a.Nev + ev) * Nz : nullptr;
+    auto zterms_at = [&](int k, double z) -> float2 {
+      if (zt) return __ldg(zt + k);
+      const double zl = (k > 0) ? zgr[k - 1] : z, zr = (k < Nz - 1) ? zgr[k + 1] : z;
+      const F32Consts fc = make_f32_consts(a.mc, P, HC, tblk);       // rare path: the precomputed terms did not fit
+      return zgrid_terms_f32(fc, make_cosmo_rate_f32(a.mc, P, HC), P, HC, a.mc.cosmo_model, z, 0.5 * (zr - zl));
+    };
+    const double fR = HC[HC_FR];
+    const double* pcompl_ev = has_cat ? a.P_compl + (size_t)ev * Nz : nullptr;
+    double like_acc = 0.0;
+    if (a.kind == CHB_PGW_1D) {
+      for (int k = tid; k < Nz; k += FU_NT) {
+        const double z = zgr[k], pg = pgw_at(z);
+        const float2 v = zterms_at(k, z);
+        like_acc += pg * (double)v.x * (double)v.y;
+        if (pout) pout[k] = pg;
+      }
+    } else if (a.catA) {
+      const double* A = a.catA + (size_t)ev * Nz;
+      const double* Bk = a.catB + (size_t)ev * Nz;
+      const double* gwp = a.gw_pdf + (size_t)ev * Pp;
+      for (int k = tid; k < Nz; k += FU_NT) {
+        const double z = zgr[k], pg = pgw_at(z);
+        const float2 v = zterms_at(k, z);
+        const double dVk = (double)v.x;
+        const double pgs = has_cat ? fR * A[k] + (1.0 - pcompl_ev[k]) * dVk * Bk[k] : dVk * Bk[k];
+        like_acc += pg * pgs * (double)v.y;
+        if (pout) for (int p = 0; p < Pp; ++p) pout[(size_t)p * Nz + k] = pg * gwp[p];
+      }
+    } else {
+      const double* gwp = a.gw_pdf + (size_t)ev * Pp;
+      const double* pcat_ev = has_cat ? a.p_cat + (size_t)ev * Pp * Nz : nullptr;
+      for (int k = tid; k < Nz; k += FU_NT) {
+        const double z = zgr[k], pg = pgw_at(z);
+        const float2 v = zterms_at(k, z);
+        const double dVk = (double)v.x, ckk = (double)v.y;
+        for (int p = 0; p < Pp; ++p) {
+          const double pv = pg * gwp[p];
+          if (pout) pout[(size_t)p * Nz + k] = pv;
+          if (p >= npix) continue;
+          const double pc = has_cat ? pcat_ev[(size_t)p * Nz + k] : 0.0;
+          if (pc == -100.0) continue;
+          const double pgal = has_cat ? fR * pc + (1.0 - pcompl_ev[k]) * dVk : dVk;
+          like_acc += pv * pgal * ckk;
+        }
+      }
+    }
+    {
+      const double ws = warp_sum(like_acc);
+      if (lane == 0) red[warp] = ws;
+      __syncthreads();
+      if (tid == 0) {
+        double like = 0.0;
+#pragma unroll
+        for (int w = 0; w < FU_NW; ++w) like += red[w];
+        a.log_like[(size_t)h * a.Nev + ev] = nan_to_num_log_fu(like); a.like_raw[(size_t)h * a.Nev + ev] = like;
+      }
+    }
+  }
+}
+
+cudaError_t numerator_fused_configure(size_t smem) {
+  return cudaFuncSetAttribute(numerator_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+int numerator_fused_ctas_per_sm(size_t smem) {
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, numerator_fused_kernel, FU_NT, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+cudaError_t launch_numerator_fused(const NumArgs& a, int grid, size_t smem, cudaStream_t s) {
+  numerator_fused_kernel<<<grid, FU_NT, smem, s>>>(a);
+  return cudaGetLastError();
+}

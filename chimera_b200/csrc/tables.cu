@@ -157,7 +157,31 @@ build_tables_kernel(ModelCfg mc, int n_hyper, const double* __restrict__ hyper, 
       if (b == 0) k = 0;
       lut[b] = (unsigned short)max(0, min(k, rc - 2));
     }
+    if (tid == 0 && !lut_ok) lut[0] = 0;            // the scan then starts at the first knot
     if (tid == 0) {
+      float* FC = reinterpret_cast<float*>(T + mc.lay.off_f32() + mc.lay.f32_fc());
+      const double inv_norm = 1.0 / HC[HC_NORM_P_M1];
+      for (int i = 0; i < CHB_NFC; ++i) FC[i] = 0.f;
+      FC[FC_LG2_M0] = (float)log2(ms[0]);
+      FC[FC_INV_LG2_MSTEP] = (float)((double)(rm - 1) / (log2(ms[rm - 1]) - log2(ms[0])));
+      FC[FC_LO] = (float)P[CHB_P_MLOW]; FC[FC_HI] = (float)P[CHB_P_MHIGH];
+      FC[FC_NEG_ALPHA] = (float)(-P[CHB_P_ALPHA]); FC[FC_BETA] = (float)P[CHB_P_BETA]; FC[FC_DM] = (float)P[CHB_P_DELTAM];
+      if (mc.mass_model == CHB_MASS_PLP) {
+        const double lam = P[CHB_P_LAMBDAP], sg = P[CHB_P_SIGMAG];
+        FC[FC_KA] = (float)log2((1.0 - lam) / HC[HC_PL_NORM] * inv_norm);
+        FC[FC_KG] = (float)log2(lam / (sg * 2.5066282746310002 * HC[HC_TG_NORM]) * inv_norm);
+        FC[FC_MU] = (float)P[CHB_P_MUG]; FC[FC_G_HI] = (float)(P[CHB_P_MUG] + 5.0 * sg);
+        FC[FC_G_C] = (float)(-1.4426950408889634 / (2.0 * sg * sg));
+      } else {
+        FC[FC_KA] = (float)log2(inv_norm);
+        if (mc.mass_model == CHB_MASS_BPL) {
+          FC[FC_KG] = (float)log2(HC[HC_BPL_RATIO] * inv_norm);
+          FC[FC_MB] = (float)HC[HC_MBREAK]; FC[FC_NEG_ALPHA2] = (float)(-P[CHB_P_ALPHA2]);
+        }
+      }
+      FC[FC_CDL_X] = (float)ms[rm - 1]; FC[FC_CDL_Y] = (float)p2[rm - 1];
+      FC[FC_LUT_B0] = __int_as_float((int)b0); FC[FC_LUT_NB] = __int_as_float(nb);
+      FC[FC_Z_TOP] = (float)zs[rc - 1];
       HC[HC_LUT_B0] = (double)b0;
       HC[HC_LUT_NB] = (double)nb;
       HC[HC_LG2_M0] = log2(ms[0]);

@@ -33,6 +33,10 @@ class Engine:
   def _chk(self, rc):
     _lib.check(rc, self.h)
 
+  def set_option(self, name, value):
+    """Per-handle tuning switch (include/chimera_b200.h: chb_set_option); results do not depend on it."""
+    self._chk(self.lib.chb_set_option(self.h, str(name).encode(), float(value)))
+
   def set_events(self, m1det, m2det, dL, pe_prior, z_grids, ra=None, dec=None):
     m1det, m2det, dL, pe_prior, z_grids, ra, dec = map(_lib.f64, (m1det, m2det, dL, pe_prior, z_grids, ra, dec))
     if dL.ndim != 2 or z_grids.ndim != 2 or z_grids.shape[0] != dL.shape[0]:

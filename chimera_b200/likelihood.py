@@ -29,7 +29,8 @@ def _bw_fields(bw_method):
 class hyperlikelihood(object):
   def __init__(self, theta_gw_det, z_grids, population, selection_function=None, kind_p_gw3d=None,
                kernel='epan', bw_method=None, cut_grid=2.0, binning=True, num_bins=200, pe_neff=2.0,
-               fp_mode='fp64', device=None, distributed=False, process_group=None, presharded=False):
+               fp_mode='fp64', device=None, distributed=False, process_group=None, presharded=False,
+               options=None):
     self.theta_gw_det = theta_gw_det
     self.population = population
     self.z_grids = np.asarray(z_grids, dtype=np.float64)
@@ -99,6 +100,8 @@ class hyperlikelihood(object):
       extra.update(sel._config_fields())
     self.cfg = model_config(population.cosmo, population.mass, population.rate, device=device, **extra)
     self.engine = Engine(self.cfg)
+    for name, value in (options or {}).items():     # per-handle tuning switches (chb_set_option); results do not depend on them
+      self.engine.set_option(name, value)
 
     t = theta_gw_det
     s = self._ev_slice

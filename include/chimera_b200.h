@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CHB_ABI_VERSION 1
+#define CHB_ABI_VERSION 2     /* 2: chb_set_option (per-handle tuning switches; no environment variables are read) */
 
 typedef enum {
   CHB_OK = 0,
@@ -104,6 +104,20 @@ const char* chb_last_error(const chb_handle* h);      /* h may be NULL: last cre
 /* hyperlikelihood(...) + selection_function(...) + population(...) construction */
 int chb_create(chb_handle** out, const chb_config* cfg);
 void chb_destroy(chb_handle* h);
+
+/* Per-handle tuning / diagnostic switches.  They select HOW the same numbers are computed (every setting is held to the
+ * same parity tests), never what; the library reads no environment variables.  No reference counterpart.
+ *   "fused"      1 (default): fp32 mode, non-pixelated / 'approximate' kinds run as ONE kernel per step with the
+ *                reweighted samples in shared memory (csrc/numerator_fused.cu); 0: reweighting kernel -> stage buffer in
+ *                global memory -> KDE kernel (csrc/numerator_f32.cu, the form the other kinds use)
+ *   "split"      1 (default) | 0: non-fused form as two kernels | as one MODE-0 kernel
+ *   "kde_win"    32 (default): windowed Gaussian recurrence, sub-stream iterations per chunk; 0: every sample visits
+ *                the whole effective grid
+ *   "kde_direct" 0 (default) | 1: one MUFU.EX2 per (grid point, sample) pair, no recurrence
+ *   "bin_runs"   1 (default) | 0: non-fused binning by runs of sorted samples | one shared-memory atomic per sample
+ *   "stage_gb"   12 (default): budget of the stage buffer of the non-fused form; hyper-points are batched beyond it
+ * Unknown names / out-of-range values: CHB_ERR_INVALID. */
+int chb_set_option(chb_handle* h, const char* name, double value);
 
 /* theta_pe_det fields (data.py:27-47) + z_grids (likelihood.py:51).  Arrays are (Nev, Ns)
  * row-major, z_grids (Nev, Nz).  ra/dec may be NULL unless kind_p_gw == CHB_PGW_FULL. */

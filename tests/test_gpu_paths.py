@@ -1,7 +1,7 @@
-"""GPU tests of the alternative code paths of the fp32 fast path: fused kernel (odd sample counts, CHB_SPLIT=0),
-hyper-point batching of the stage buffer (CHB_STAGE_GB), windows switched off (CHB_KDE_WIN=0, short z grids) and
-the one-MUFU-per-pair pair sums (CHB_KDE_DIRECT=1) -- all against the NumPy oracle on the same seeded inputs."""
-import os
+"""GPU tests of the alternative code paths of the fp32 mode, selected per handle with chb_set_option (`options=`):
+the fused one-kernel form of the 1-D kinds (default) with and without windows, the round-1 split / MODE-0 kernels
+(`fused=0`), odd sample counts, hyper-point batching of the stage buffer, one-MUFU-per-pair sums -- all against the
+NumPy oracle on the same seeded inputs; plus two handles of different shapes interleaved in one process."""
 import numpy as np
 import pytest
 
@@ -40,38 +40,63 @@ def _check(lle, ref, tol=2e-5):
   assert err < tol, err
 
 
-@pytest.mark.parametrize("ns,nz,env", [
-  (4097, 300, {}),                          # odd sample count: fused kernel, recurrence without windows
-  (4096, 300, {"CHB_SPLIT": "0"}),          # fused kernel with the windowed KDE
-  (4096, 300, {"CHB_KDE_WIN": "0"}),        # split kernels, full-grid recurrence
-  (4096, 300, {"CHB_KDE_DIRECT": "1"}),     # one MUFU.EX2 per pair
-  (4096, 300, {"CHB_STAGE_GB": "0.0003"}),  # stage buffer for ONE hyper-point at a time: three batches
-  (4096, 48, {}),                           # z grid too short for the chunk tables: no windows
-  (4096, 300, {}),                          # default: split + windows + packed FP32
+@pytest.mark.parametrize("ns,nz,opt", [
+  (4096, 300, {}),                                   # default: fused kernel, windowed recurrence on the raw stage
+  (4096, 300, {"kde_win": 0}),                       # fused kernel, direct pair sums (no window plan)
+  (4096, 48, {}),                                    # z grid too short for a window plan
+  (700, 300, {}),                                    # few samples: ragged last block, < 8 chunks -> direct sums
+  (4097, 300, {}),                                   # odd sample count: round-1 MODE-0 kernel, recurrence without windows
+  (4096, 300, {"fused": 0}),                         # round-1 split kernels + windows
+  (4096, 300, {"fused": 0, "split": 0}),             # round-1 MODE-0 kernel with the windowed KDE
+  (4096, 300, {"fused": 0, "kde_win": 0}),           # split kernels, full-grid recurrence
+  (4096, 300, {"fused": 0, "kde_direct": 1}),        # one MUFU.EX2 per pair
+  (4096, 300, {"fused": 0, "stage_gb": 0.0003}),     # stage buffer for ONE hyper-point at a time: three batches
 ])
-def test_fast_path_variants_match_oracle(cb, ns, nz, env):
+def test_fast_path_variants_match_oracle(cb, ns, nz, opt):
   th, zg, pop, sel, H0, ref = _case(cb, ns, nz)
-  old = {k: os.environ.get(k) for k in env}
-  os.environ.update(env)
-  try:
-    like = cb.hyperlikelihood(th, zg, pop, sel, kernel="gauss", binning=False, fp_mode="fp32")
-    lle = like.compute_all(H0=H0)[0]
-    lle2 = like.compute_all(H0=H0)[0]
-  finally:
-    for k, v in old.items():
-      if v is None:
-        os.environ.pop(k, None)
-      else:
-        os.environ[k] = v
+  like = cb.hyperlikelihood(th, zg, pop, sel, kernel="gauss", binning=False, fp_mode="fp32", options=opt)
+  lle = like.compute_all(H0=H0)[0]
+  lle2 = like.compute_all(H0=H0)[0]
   _check(lle, ref)
   np.testing.assert_array_equal(lle, lle2)      # bit-reproducible from call to call
+
+
+@pytest.mark.parametrize("kernel,binning,bw", [("epan", True, None), ("gauss", True, "silverman"), ("epan", False, 0.3),
+                                               ("gauss", False, "silverman"), ("gauss", False, 0.25)])
+def test_fused_kernel_kde_options(cb, kernel, binning, bw):
+  """Every KDE option of the 1-D kinds through the fused kernel and through the round-1 kernels, against the oracle."""
+  from oracle import chimera_oracle as orc
+  th, zg, pop, sel, H0, _ = _case(cb, 2048, 200, nev=8, seed=431)
+  from chimera_b200 import synth
+  ev = synth.make_events(8, 2048, seed=431, sky=False)
+  inj, N_inj = synth.make_injections(20000, seed=432)
+  pop0 = orc.make_pop(orc.make_cosmo("flrw", z_max=5.), orc.make_mass("plp"), orc.make_rate("madau_dickinson"))
+  opts = orc.make_opts(None, kernel, bw, 2.0, binning, 200, 2.0)
+  ref = np.array([orc.compute_all(pop0, ev, zg, opts, inj, N_inj, 5., None, H0=float(h))[0] for h in H0])
+  for opt in ({}, {"fused": 0}):
+    like = cb.hyperlikelihood(th, zg, pop, sel, kernel=kernel, bw_method=bw, binning=binning, num_bins=200,
+                              fp_mode="fp32", options=opt)
+    _check(like.compute_all(H0=H0)[0], ref, tol=1e-4)
+
+
+def test_two_handles_interleaved(cb):
+  """Handles with different shared-memory footprints alternate in one process (the kernels' dynamic shared-memory
+  attribute is process-wide): neither may invalidate the other's launches, in either path."""
+  big = _case(cb, 4096, 300)
+  small = _case(cb, 512, 64, nev=6, seed=77)
+  for opt in ({}, {"fused": 0}):
+    la = cb.hyperlikelihood(big[0], big[1], big[2], big[3], kernel="gauss", binning=False, fp_mode="fp32", options=opt)
+    lb = cb.hyperlikelihood(small[0], small[1], small[2], small[3], kernel="gauss", binning=False, fp_mode="fp32", options=opt)
+    for _ in range(2):
+      _check(la.compute_all(H0=big[4])[0], big[5])
+      _check(lb.compute_all(H0=small[4])[0], small[5])
 
 
 @pytest.mark.parametrize("kind,kernel,binning", [("approximate", "gauss", False), ("marginalized", "epan", False),
                                                  ("marginalized", "epan", True), ("full", "gauss", False)])
 def test_fused_kernel_pixelated_kinds(cb, kind, kernel, binning):
-  """CHB_SPLIT=0 routes the pixelated kinds through the fused kernel (numerator_f32_kernel<KG, 0>); it must agree
-  with the oracle like the split form does (tests/test_gpu_parity.py)."""
+  """`split=0` routes the pixelated kinds through the one-kernel MODE-0 form (numerator_f32_kernel<KG, 0>); it must
+  agree with the oracle like the split form does (tests/test_gpu_parity.py)."""
   from oracle import chimera_oracle as orc
   from test_gpu_parity import _synthetic
   ev, zg, inj, N_inj, cat = _synthetic(12, 1500, 120, 20000, True, seed=107)
@@ -84,15 +109,7 @@ def test_fused_kernel_pixelated_kinds(cb, kind, kernel, binning):
   opts = orc.make_opts(kind, kernel, None, 2.0, binning, 200, 2.0)
   H0 = np.array([60., 75.])
   ref = np.array([orc.compute_all(pop0, ev, zg, opts, inj, N_inj, 5., ev["neff_pixels"], H0=float(h))[0] for h in H0])
-  old = os.environ.get("CHB_SPLIT")
-  os.environ["CHB_SPLIT"] = "0"
-  try:
-    like = cb.hyperlikelihood(cb.theta_pe_det(**kw), zg, pop, sel, kind_p_gw3d=kind, kernel=kernel, binning=binning,
-                              num_bins=200, fp_mode="fp32")
-    lle = like.compute_all(H0=H0)[0]
-  finally:
-    if old is None:
-      os.environ.pop("CHB_SPLIT", None)
-    else:
-      os.environ["CHB_SPLIT"] = old
+  like = cb.hyperlikelihood(cb.theta_pe_det(**kw), zg, pop, sel, kind_p_gw3d=kind, kernel=kernel, binning=binning,
+                            num_bins=200, fp_mode="fp32", options={"fused": 0, "split": 0})
+  lle = like.compute_all(H0=H0)[0]
   _check(lle, ref, tol=1e-4)
