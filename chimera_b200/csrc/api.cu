@@ -43,6 +43,7 @@ struct chb_handle {
   std::string err;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t evz = nullptr;               // after the z-grid terms (start of the numerator kernels proper)
   int sm_count = 148;
   int max_smem_optin = 0;
   int64_t launches = 0;
@@ -159,6 +160,7 @@ int chb_create(chb_handle** out, const chb_config* cfg) {
   if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
     delete h; return cuda_fail(nullptr, e, "cudaStreamCreate"); }
   for (auto& evn : h->ev) cudaEventCreate(&evn);
+  cudaEventCreate(&h->evz);
   *out = h;
   return CHB_OK;
 }
@@ -175,6 +177,7 @@ void chb_destroy(chb_handle* h) {
   h->s4.release(); h->l2.release(); h->inj_s4.release(); h->inj_l2.release(); h->zterms.release(); h->zw_stage.release(); h->unit_stats.release(); h->catA.release(); h->catB.release();
   h->neff_pix.release();
   for (auto& evn : h->ev) if (evn) cudaEventDestroy(evn);
+  if (h->evz) cudaEventDestroy(h->evz);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -367,6 +370,7 @@ static int eval_impl(chb_handle* h, int64_t n_hyper, const double* d_hyper, doub
   CU(launch_build_tables(h->mc, (int)n_hyper, d_hyper, h->tabs.p, h->HC.p, s), "build_tables launch");
   h->launches++;
   cudaEventRecord(h->ev[1], s);
+  cudaEventRecord(h->evz, s);
 
   double* ll = nullptr;
   if (do_num) {
@@ -411,9 +415,10 @@ static int eval_impl(chb_handle* h, int64_t n_hyper, const double* d_hyper, doub
       // The dynamic-shared-memory attribute of a kernel is process-wide: it is only ever set to the device maximum
       // (never to a handle's own footprint), so handles with different shapes cannot invalidate each other's launches.
       const int optin = h->max_smem_optin;
+      const size_t fit = (size_t)optin - 1024;     // dynamic footprints must leave room for the kernels' static shared memory
       // (1) 1-D kinds: ONE fused kernel per step (numerator_fused.cu), samples never leave shared memory.
       const size_t ff = numerator_fused_smem_bytes(a);
-      bool fused = h->opt_fused && numerator_fused_supported(a) && ff <= (size_t)optin;
+      bool fused = h->opt_fused && numerator_fused_supported(a) && ff <= fit;
       if (fused && h->fused_per < 0) {
         h->fused_per = (numerator_fused_configure(optin) == cudaSuccess) ? numerator_fused_ctas_per_sm(ff) : 0;
         cudaGetLastError();
@@ -423,7 +428,7 @@ static int eval_impl(chb_handle* h, int64_t n_hyper, const double* d_hyper, doub
       // KDE/z-integral kernel; fused MODE 0 kernel for odd Ns or when there is no memory for the stage.
       size_t fs = numerator_f32_smem_bytes(a, 0);
       const size_t fs1 = numerator_f32_smem_bytes(a, 1), fs2 = numerator_f32_smem_bytes(a, 2);
-      bool split = !fused && h->opt_split && (h->Ns % 2 == 0) && fs2 <= (size_t)optin && fs1 <= (size_t)optin;
+      bool split = !fused && h->opt_split && (h->Ns % 2 == 0) && fs2 <= fit && fs1 <= fit;
       int64_t nb = n_hyper;                        // hyper-points per batch of the split form
       if (split) {
         // the plan (batch size, stage buffers, occupancy) is cached per n_hyper and reset by chb_set_* / chb_set_option:
@@ -449,7 +454,7 @@ static int eval_impl(chb_handle* h, int64_t n_hyper, const double* d_hyper, doub
         nb = h->plan_nb;
         split = h->plan_ok;
       }
-      if (fused || split || fs <= (size_t)optin) {
+      if (fused || split || fs <= fit) {
         // z-grid terms for all (hyper-point, event, k) in one full-occupancy pass when they fit in 2 GiB
         const size_t zt_elems = (size_t)n_hyper * h->Nev * h->Nz;
         a.zterms = nullptr; a.zterms_out = nullptr; a.zterms_h0 = 0;
@@ -459,6 +464,7 @@ static int eval_impl(chb_handle* h, int64_t n_hyper, const double* d_hyper, doub
           CU(launch_zgrid_terms(a, 0, (int)n_hyper, s), "zgrid_terms launch");
           h->launches++;
           a.zterms = h->zterms.p;
+          cudaEventRecord(h->evz, s);
         }
         if (fused) {
           const int grid = (int)std::min<long long>(units, (long long)h->sm_count * h->fused_per);
@@ -727,15 +733,19 @@ int chb_phase_profile(chb_handle* h, int enable, double out[8]) {
 
 int64_t chb_kernel_launch_count(const chb_handle* h) { return h ? h->launches : 0; }
 
-int chb_last_timings(const chb_handle* h, double out[4]) {
+int chb_last_timings(const chb_handle* h, double out[8]) {
   if (!h || !out) return CHB_ERR_INVALID;
   cudaSetDevice(h->cfg.device);
   if (cudaEventSynchronize(h->ev[4]) != cudaSuccess) { cudaGetLastError(); return CHB_ERR_STATE; }
+  for (int i = 0; i < 8; ++i) out[i] = 0.0;
   for (int i = 0; i < 4; ++i) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]) != cudaSuccess) { cudaGetLastError(); return CHB_ERR_STATE; }
     out[i] = ms;
   }
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, h->ev[1], h->evz) == cudaSuccess) out[4] = ms; else cudaGetLastError();
+  if (cudaEventElapsedTime(&ms, h->evz, h->ev[2]) == cudaSuccess) out[5] = ms; else cudaGetLastError();
   return CHB_OK;
 }
 

@@ -776,9 +776,15 @@ static inline int kind_group(int kind) { return kind == CHB_PGW_MARG ? 1 : (kind
     case 7: { auto kern = numerator_f32_kernel<2, 1, F_NT>; EXPR; } break;                           \
     default: { auto kern = numerator_f32_kernel<2, 2, F_NT>; EXPR; } break;                          \
   }
-cudaError_t numerator_f32_configure(int kind, int mode, size_t smem) {
+// `optin`: the device's opt-in maximum of shared memory per block; the attribute is set to that maximum minus the kernel's
+// static shared memory (the limit applies to static + dynamic), never to a handle's own footprint.
+cudaError_t numerator_f32_configure(int kind, int mode, size_t optin) {
   cudaError_t e = cudaSuccess;
-  CHB_F32_DISPATCH(kind_group(kind), mode, e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaFuncAttributes fa;
+  CHB_F32_DISPATCH(kind_group(kind), mode, {
+    e = cudaFuncGetAttributes(&fa, kern);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(optin - fa.sharedSizeBytes));
+  });
   return e;
 }
 int numerator_f32_ctas_per_sm(int kind, int mode, size_t smem) {

@@ -576,8 +576,11 @@ numerator_fused_kernel(const NumArgs a) {
   }
 }
 
-cudaError_t numerator_fused_configure(size_t smem) {
-  return cudaFuncSetAttribute(numerator_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+cudaError_t numerator_fused_configure(size_t optin) {      // see numerator_f32_configure
+  cudaFuncAttributes fa;
+  cudaError_t e = cudaFuncGetAttributes(&fa, numerator_fused_kernel);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(numerator_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(optin - fa.sharedSizeBytes));
 }
 int numerator_fused_ctas_per_sm(size_t smem) {
   int n = 0;

@@ -119,6 +119,7 @@ class Engine:
     return int(self.lib.chb_kernel_launch_count(self.h))
 
   def timings(self):
-    t = np.zeros(4)
+    t = np.zeros(8)
     self.lib.chb_last_timings(self.h, _lib.dptr(t))
-    return dict(tables_ms=t[0], numerator_ms=t[1], selection_ms=t[2], reduce_ms=t[3])
+    return dict(tables_ms=t[0], numerator_ms=t[1], selection_ms=t[2], reduce_ms=t[3], zgrid_terms_ms=t[4],
+                numerator_kernels_ms=t[5])

@@ -30,7 +30,7 @@ class hyperlikelihood(object):
   def __init__(self, theta_gw_det, z_grids, population, selection_function=None, kind_p_gw3d=None,
                kernel='epan', bw_method=None, cut_grid=2.0, binning=True, num_bins=200, pe_neff=2.0,
                fp_mode='fp64', device=None, distributed=False, process_group=None, presharded=False,
-               options=None):
+               options=None, hyper_groups=1):
     self.theta_gw_det = theta_gw_det
     self.population = population
     self.z_grids = np.asarray(z_grids, dtype=np.float64)
@@ -69,15 +69,22 @@ class hyperlikelihood(object):
     # otherwise every rank holds the global arrays and keeps its contiguous chunk.
     self.rank, self.world = parallel.dist_info(process_group) if distributed else (0, 1)
     self.group = process_group
+    # 2-D layout (hyper_groups > 1): ranks in one hyper group split the events/injections, the groups split the
+    # hyper-points of every batch (the reference's 'both' scheme, CHIMERA/parallel.py:132-229) -- for walker batches
+    # so large that rebuilding every table and every z-grid term on every rank would dominate (C5: 4096 points).
+    self.hyper_groups = int(hyper_groups)
+    self._eshard, self._nshards, self._hgroup = parallel.grid_coords(self.rank, self.world, self.hyper_groups)
     self.presharded = bool(presharded) and self.world > 1
     if self.presharded:
+      if self.hyper_groups != 1:
+        raise ValueError("presharded inputs and hyper_groups > 1 cannot be combined")
       self._ev_counts = parallel.allgather_counts(self.nevents, process_group)
       lo, hi = 0, self.nevents
       self.nevents = int(sum(self._ev_counts))
     else:
-      self._ev_counts = [parallel.shard_bounds(self.nevents, r, self.world) for r in range(self.world)]
+      self._ev_counts = [parallel.shard_bounds(self.nevents, r, self._nshards) for r in range(self._nshards)]
       self._ev_counts = [b - a for a, b in self._ev_counts]
-      lo, hi = parallel.shard_bounds(self.nevents, self.rank, self.world)
+      lo, hi = parallel.shard_bounds(self.nevents, self._eshard, self._nshards)
     self._ev_slice = slice(lo, hi)
     if device is None:
       device = 0
@@ -117,32 +124,67 @@ class hyperlikelihood(object):
     if sel is not None:
       ti = sel.theta_inj_det
       arrs = [np.ravel(np.asarray(x, dtype=np.float64)) for x in (ti.m1det, ti.m2det, ti.dL, ti.p_draw)]
-      ilo, ihi = (0, arrs[0].size) if self.presharded else parallel.shard_bounds(arrs[0].size, self.rank, self.world)
+      ilo, ihi = (0, arrs[0].size) if self.presharded else parallel.shard_bounds(arrs[0].size, self._eshard, self._nshards)
       if ihi > ilo:
         self.engine.set_injections(*[a[ilo:ihi] for a in arrs])
+    self._has_work = (hi > lo) or (sel is not None and ihi > ilo)      # an empty shard contributes zero partials
 
   # ---- evaluation core ---------------------------------------------------------------------
   def _evaluate(self, pop_lambdas, want_events=False, want_pgw=False):
     rows, batched = pop_lambdas.hyper_rows()
-    lle, part, pgw = self.engine.eval(rows, want_events=want_events, want_pgw=want_pgw)
-    if self.world > 1:
+    n = rows.shape[0]
+    if self.world == 1:
+      lle, part, pgw = self.engine.eval(rows, want_events=want_events, want_pgw=want_pgw)
+    elif not want_events and parallel.backend(self.group) == "nccl":
+      # NCCL: the partials stay on the device from the kernels through the all-reduce; one D2H copy of (n, 3)
+      import torch
+      dev = torch.device("cuda", self.cfg.device)
+      d_rows = torch.from_numpy(np.ascontiguousarray(rows)).to(dev)
+      d_part = torch.zeros((n, 3), dtype=torch.float64, device=dev)
+      with torch.cuda.device(dev):
+        self.partials_device(d_rows, d_part)
+        part = d_part.cpu().numpy()
+      lle, pgw = None, None
+    else:
+      # this rank's hyper-points (all of them unless hyper_groups > 1) on this rank's events and injections
+      hlo, hhi = parallel.shard_bounds(n, self._hgroup, self.hyper_groups)
+      part = np.zeros((n, 3))
+      lle, pgw = None, None
+      nev_loc = self.engine.Nev
+      if want_events:
+        lle = np.zeros((n, nev_loc))
+      if self._has_work and hhi > hlo:
+        l, p, _ = self.engine.eval(rows[hlo:hhi], want_events=want_events, want_pgw=False)
+        part[hlo:hhi] = p
+        if want_events and l is not None:
+          lle[hlo:hhi] = l
       part = parallel.allreduce_partials(part, self.group)
       if want_events:
-        if lle is None:
-          lle = np.zeros((rows.shape[0], 0))
-        lle = parallel.allgather_events(lle, self._ev_counts, self.group)
+        # per-event values: gather the event shards; with hyper groups the zero-filled blocks of the other groups add up
+        lle = parallel.allgather_events(lle, self._ev_counts * self.hyper_groups if self.hyper_groups > 1 else self._ev_counts,
+                                        self.group)
+        if self.hyper_groups > 1:
+          E = sum(self._ev_counts)
+          lle = sum(lle[:, g * E:(g + 1) * E] for g in range(self.hyper_groups))
     fin = self.engine.finalize(rows, part, self.nevents)
     return rows, batched, lle, part, pgw, fin
 
   def partials_device(self, d_rows, d_partials, stream=None):
-    """Device-resident entry (torch f64 CUDA tensors): rows (n, CHB_NPAR) -> partials (n, 3), summed
-    over ranks with one NCCL all-reduce when distributed.  Asynchronous on torch's current stream."""
+    """Device-resident entry (torch f64 CUDA tensors): rows (n, CHB_NPAR) -> partials (n, 3), summed over ranks with
+    one NCCL all-reduce when distributed (no host round trip).  Asynchronous on torch's current stream."""
     import torch
     st = torch.cuda.current_stream().cuda_stream if stream is None else stream
     st = st or 1      # 0 is the legacy default stream: name it explicitly (cudaStreamLegacy), NULL means 'handle stream'
-    self.engine.eval_device(d_rows, d_partials, None, st)
-    if self.world > 1:
-      parallel.allreduce_partials(d_partials, self.group)
+    if self.world == 1:
+      self.engine.eval_device(d_rows, d_partials, None, st)
+      return d_partials
+    n = d_rows.shape[0]
+    hlo, hhi = parallel.shard_bounds(n, self._hgroup, self.hyper_groups)
+    if hlo > 0 or hhi < n or not self._has_work:
+      d_partials.zero_()
+    if self._has_work and hhi > hlo:
+      self.engine.eval_device(d_rows[hlo:hhi], d_partials[hlo:hhi], None, st)
+    parallel.allreduce_partials(d_partials, self.group)
     return d_partials
 
   @staticmethod

@@ -1,5 +1,5 @@
-"""Multi-GPU plumbing: one process per GPU, events and injections sharded contiguously, one
-all-reduce of the per-rank partials.
+"""Multi-GPU plumbing: one process per GPU, events and injections sharded contiguously (optionally hyper-points
+too: `grid_coords`), one all-reduce of the per-rank partials.
 
 The split rule is the reference's (CHIMERA/parallel.py:68-73, 94-99: `n // R` per rank, the first
 `n % R` ranks get one more).  The exchanged payload is `(n_hyper, 3)` f64 =
@@ -15,6 +15,20 @@ def shard_bounds(n, rank, world):
   return lo, lo + base + (1 if rank < rem else 0)
 
 
+def grid_coords(rank, world, hyper_groups=1):
+  """2-D layout for large walker batches (the reference's 'both' scheme, CHIMERA/parallel.py:132-229): the world is
+  `hyper_groups` groups of `world // hyper_groups` ranks.  Returns (event_shard, n_event_shards, hyper_group).
+  A rank owns event/injection shard `event_shard` and evaluates only the hyper-points of `hyper_group`
+  (`shard_bounds(n_hyper, hyper_group, hyper_groups)`); every (hyper-point, event) unit and every
+  (hyper-point, injection) pair is evaluated by exactly one rank, so ONE SUM all-reduce of the zero-filled
+  (n_hyper, 3) partials over the whole world still gives the global sums."""
+  k = int(hyper_groups)
+  if k < 1 or world % k != 0:
+    raise ValueError(f"hyper_groups={k} must divide the world size {world}")
+  E = world // k
+  return rank % E, E, rank // E
+
+
 def dist_info(group=None):
   """(rank, world) of the torch.distributed group, or (0, 1) when not initialised."""
   try:
@@ -24,6 +38,17 @@ def dist_info(group=None):
   if not (dist.is_available() and dist.is_initialized()):
     return 0, 1
   return dist.get_rank(group), dist.get_world_size(group)
+
+
+def backend(group=None):
+  """Name of the torch.distributed backend in use ('' when not initialised)."""
+  try:
+    import torch.distributed as dist
+  except Exception:
+    return ""
+  if not (dist.is_available() and dist.is_initialized()):
+    return ""
+  return dist.get_backend(group)
 
 
 def allgather_counts(n_local, group=None):

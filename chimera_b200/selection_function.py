@@ -8,7 +8,10 @@ from .population._base import model_config
 
 
 class selection_function(object):
-  def __init__(self, theta_inj_det, N_inj, N_eff=5., device=None):
+  def __init__(self, theta_inj_det, N_inj, N_eff=5., device=None, fp_mode='fp64'):
+    if fp_mode not in _lib.FP_IDS:
+      raise ValueError("fp_mode must be 'fp64' or 'fp32'")
+    self.fp_mode = fp_mode                 # arithmetic of the stand-alone N_exp (the likelihood's own handle has its fp_mode)
     self.theta_inj_det = theta_inj_det
     self.N_inj = N_inj
     self.N_eff = N_eff
@@ -24,7 +27,7 @@ class selection_function(object):
            float(pop.Tobs), bool(pop.scale_free))
     if key not in self._engines:
       cfg = model_config(pop.cosmo, pop.mass, pop.rate, device=self.device or 0, Tobs=float(pop.Tobs),
-                         scale_free=int(bool(pop.scale_free)), **self._config_fields())
+                         scale_free=int(bool(pop.scale_free)), fp_mode=_lib.FP_IDS[self.fp_mode], **self._config_fields())
       eng = Engine(cfg)
       t = self.theta_inj_det
       eng.set_injections(t.m1det, t.m2det, t.dL, t.p_draw)

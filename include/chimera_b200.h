@@ -198,9 +198,10 @@ int chb_model_tables(const chb_config* cfg, const double* params, double* z_grid
 
 /* Introspection for benchmarks/tests: launches of this library's kernels since creation. */
 int64_t chb_kernel_launch_count(const chb_handle* h);
-/* Device time (ms, CUDA events on the handle's stream) of the last chb_eval*'s kernels:
- * out[0]=tables, out[1]=numerator (reweight+KDE+z-integral), out[2]=selection, out[3]=reduce */
-int chb_last_timings(const chb_handle* h, double out[4]);
+/* Device time (ms, CUDA events on the launching stream) of the last chb_eval*'s kernels:
+ * out[0]=tables, out[1]=numerator incl. z-grid terms, out[2]=selection, out[3]=reduce,
+ * out[4]=z-grid terms alone, out[5]=reweight+KDE+z-integral kernel(s) alone, out[6..7]=0 (reserved) */
+int chb_last_timings(const chb_handle* h, double out[8]);
 
 /* Phase profile of the fused numerator kernel: mean SM-clock cycles per CTA spent in
  * [0] table staging, [1] z-grid terms, [2] reweighting, [3] statistics/grid, [4] KDE+integrand,

@@ -34,6 +34,11 @@ def golden_like():
 
 
 @pytest.fixture(scope="session")
+def golden_like2():
+  return load_golden("golden_like2.npz")
+
+
+@pytest.fixture(scope="session")
 def golden_in1d():
   return load_golden("golden_inputs_1d.npz")
 

@@ -214,6 +214,44 @@ def gen_like():
   save("golden_like.npz", **out)
 
 
+def gen_like2():
+  """Round 2: the model / option matrix of tests/cases.py LIKE_CASES2 on the SAME inputs as gen_like (same seeds), written to
+  golden_like2.npz; the round-1 fixtures are left byte-identical."""
+  from cases import LIKE_CASES2
+  ev1, zg1, inj, N_inj = build_inputs(nev=10, ns=400, nz=60, ninj=3000, sky=False, seed=11)
+  evp, zgp, _, _ = build_inputs(nev=6, ns=500, nz=50, ninj=10, sky=True, seed=21)
+  gal = synth.make_galaxies(60_000, seed=31)
+  rcatalog.load_galaxy_catalog = lambda fname, backend="numpy": dict(ra=gal["ra"], dec=gal["dec"], z=gal["z"])
+  fid = CH.cosmo.flrw(H0=70., Om0=0.25, z_max=5.)
+  thp = ref_theta(evp, True)
+  gcat = rcatalog.pixelated_catalog(completeness=dVdz_completeness([0.073, 1.3]), cosmo=fid,
+                                    z_grids=J(zgp), fname_data_gal="synthetic", data_gw_pixelated=thp, z_err=0.001)
+  sel = CH.selection_function(theta_inj_det(m1det=J(inj["m1det"]), m2det=J(inj["m2det"]), dL=J(inj["dL"]),
+                                            p_draw=J(inj["p_draw"])), N_inj, 5.)
+  out = {}
+  for name, c in LIKE_CASES2.items():
+    pix = c["kind"] is not None
+    ev, zg = (evp, zgp) if pix else (ev1, zg1)
+    th = thp if pix else ref_theta(ev, False)
+    cosmo = getattr(CH.cosmo, c["cosmo"][0])(H0=70., Om0=0.25, z_max=5., **c["cosmo"][1])
+    mass = getattr(CH.mass, c["mass"][0])(**c["mass"][1])
+    rate = getattr(CH.rate, c["rate"][0])(**c["rate"][1])
+    pop = CH.population(cosmo, mass, rate, gal_cat=gcat if pix else None)
+    like = CH.hyperlikelihood(th, J(zg), pop, sel, kind_p_gw3d=c["kind"], kernel=c["kernel"], bw_method=c["bw"],
+                              binning=c["binning"], num_bins=40, pe_neff=2.0, cut_grid=2.0)
+    for h, hl in enumerate(c["hypers"]):
+      lle, lnum, lnexp, lh = like.compute_all(**hl)
+      out[f"{name}_h{h}_lle"] = np.asarray(lle)
+      out[f"{name}_h{h}_tot"] = np.array([lnum, lnexp, lh], dtype=np.float64)
+    out[f"{name}_nh"] = np.int64(len(c["hypers"]))
+    print(name, [float(out[f"{name}_h{h}_tot"][2]) for h in range(len(c["hypers"]))])
+  # selection function alone, bpl + mg_flrw + truncated rate (the fp32 selection kernel had never been compared with bpl)
+  pop = CH.population(CH.cosmo.mg_flrw(H0=70., Om0=0.25, z_max=5.), CH.mass.bpl(), CH.rate.trunc_madau_dickinson(zmax=2.0))
+  hs = [dict(H0=60., Xi0=0.7, n=1.9), dict(H0=70., Xi0=1.0, n=0.), dict(H0=82., Xi0=1.8, n=2.3, alpha_1=2.0, break_fraction=0.3)]
+  out["sel_bpl_mg_nexp"] = np.array([float(sel.N_exp(pop.update(**hl))) for hl in hs])
+  save("golden_like2.npz", **out)
+
+
 def gen_setup():
   ev, zg, _, _ = build_inputs(nev=5, ns=300, nz=40, ninj=10, sky=True, seed=51)
   out = dict(dL=ev["dL"], ra=ev["ra"], dec=ev["dec"])
@@ -239,6 +277,10 @@ def gen_setup():
 
 
 if __name__ == "__main__":
+  if "--like2" in sys.argv:      # round 2: only the new fixture (the round-1 files stay byte-identical)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    gen_like2()
+    sys.exit(0)
   gen_models()
   gen_math()
   gen_like()

@@ -95,3 +95,62 @@ def test_two_rank_gloo_matches_single_process():
     for i in range(3):
       np.testing.assert_allclose(lle_all[i], ref[i][0], rtol=1e-13)
       np.testing.assert_allclose(lh[i], ref[i][3], rtol=1e-12)
+
+
+def _worker_2d(rank, world, port, q):
+  """4 ranks = 2 event shards x 2 hyper groups (the reference's 'both' scheme, CHIMERA/parallel.py:132-229)."""
+  import torch.distributed as dist
+  os.environ["MASTER_ADDR"] = "127.0.0.1"
+  os.environ["MASTER_PORT"] = str(port)
+  dist.init_process_group("gloo", rank=rank, world_size=world)
+  try:
+    from chimera_b200 import parallel, synth
+    ev = synth.make_events(7, 300, seed=5)
+    ev = {k: ev[k] for k in ("m1det", "m2det", "dL", "pe_prior")}
+    zg = synth.make_z_grids(ev["dL"], 60, H0_prior=(40., 120.))
+    inj, N_inj = synth.make_injections(2001, seed=6)
+    hypers = [dict(H0=60.), dict(H0=70.), dict(H0=83.)]
+    ei, E, gi = parallel.grid_coords(rank, world, hyper_groups=2)
+    lo, hi = parallel.shard_bounds(7, ei, E)
+    ilo, ihi = parallel.shard_bounds(2001, ei, E)
+    hlo, hhi = parallel.shard_bounds(len(hypers), gi, 2)
+    part = np.zeros((len(hypers), 3))
+    lle = np.zeros((len(hypers), hi - lo))
+    l, p = _partials_oracle(ev, zg, inj, N_inj, hypers[hlo:hhi], lo, hi, ilo, ihi)
+    part[hlo:hhi] = p
+    lle[hlo:hhi] = l
+    part = parallel.allreduce_partials(part)
+    counts = [b - a for a, b in (parallel.shard_bounds(7, r, E) for r in range(E))]
+    lle_all = parallel.allgather_events(lle, counts * 2)
+    lle_all = lle_all[:, :7] + lle_all[:, 7:]
+    q.put((rank, (ei, E, gi), part, lle_all))
+  finally:
+    dist.destroy_process_group()
+
+
+def test_four_rank_2d_sharding_matches_single_process():
+  import torch.multiprocessing as mp
+  from chimera_b200 import synth, parallel
+  assert [parallel.grid_coords(r, 8, 2) for r in range(8)] == [(0, 4, 0), (1, 4, 0), (2, 4, 0), (3, 4, 0),
+                                                                (0, 4, 1), (1, 4, 1), (2, 4, 1), (3, 4, 1)]
+  with pytest.raises(ValueError):
+    parallel.grid_coords(0, 8, 3)
+  ctx = mp.get_context("spawn")
+  q = ctx.Queue()
+  port = _free_port()
+  procs = [ctx.Process(target=_worker_2d, args=(r, 4, port, q)) for r in range(4)]
+  for p in procs:
+    p.start()
+  res = [q.get(timeout=240) for _ in procs]
+  for p in procs:
+    p.join(timeout=60)
+    assert p.exitcode == 0
+  ev = synth.make_events(7, 300, seed=5)
+  ev = {k: ev[k] for k in ("m1det", "m2det", "dL", "pe_prior")}
+  zg = synth.make_z_grids(ev["dL"], 60, H0_prior=(40., 120.))
+  inj, N_inj = synth.make_injections(2001, seed=6)
+  hypers = [dict(H0=60.), dict(H0=70.), dict(H0=83.)]
+  lle_ref, part_ref = _partials_oracle(ev, zg, inj, N_inj, hypers, 0, 7, 0, 2001)
+  for rank, coords, part, lle_all in res:
+    np.testing.assert_allclose(part, part_ref, rtol=1e-12)
+    np.testing.assert_allclose(lle_all, lle_ref, rtol=1e-13)

@@ -4,7 +4,7 @@ only differences are operation order) unless stated."""
 import numpy as np
 import pytest
 from oracle import chimera_oracle as orc
-from cases import COSMO_CASES, MASS_CASES, RATE_CASES, LIKE_CASES, GOLDEN_NUM_BINS
+from cases import LIKE_CASES2, SEL_BPL_MG_HYPERS, COSMO_CASES, MASS_CASES, RATE_CASES, LIKE_CASES, GOLDEN_NUM_BINS
 
 RTOL = 1e-12
 
@@ -120,6 +120,33 @@ def test_likelihood(golden_like, golden_in1d, golden_inpix, name):
       pgw = orc.p_gw3dfull(pop, ev, zg, opts, npx)
     scale = np.nanmax(np.abs(golden_like[f"{name}_h{h}_pgw"]))
     close(pgw, golden_like[f"{name}_h{h}_pgw"], rtol=1e-9, atol=1e-12 * scale)
+
+
+@pytest.mark.parametrize("name", list(LIKE_CASES2))
+def test_likelihood_model_matrix(golden_like2, golden_in1d, golden_inpix, name):
+  """tpl / bpl masses, power-law and truncated rates, silverman / scalar bandwidths, curved and w0-wa cosmologies,
+  mg_flrw with a catalogue: the oracle against the reference's own outputs (tests/golden/make_golden.py --like2)."""
+  c = LIKE_CASES2[name]
+  pix = c["kind"] is not None
+  g = golden_inpix if pix else golden_in1d
+  ev, zg, inj, N_inj = _inputs(g, pix)
+  cat = dict(p_cat=g["p_cat"], P_compl=g["P_compl"], z_range=g["z_range"]) if pix else None
+  pop0 = orc.make_pop(orc.make_cosmo(c["cosmo"][0], H0=70., Om0=0.25, z_max=5., **c["cosmo"][1]),
+                      orc.make_mass(c["mass"][0], **c["mass"][1]), orc.make_rate(c["rate"][0], **c["rate"][1]), catalog=cat)
+  opts = orc.make_opts(c["kind"], c["kernel"], c["bw"], 2.0, c["binning"], GOLDEN_NUM_BINS, 2.0)
+  npx = g["neff_pixels"] if pix else None
+  for h, hl in enumerate(c["hypers"]):
+    lle, lnum, lnexp, lh = orc.compute_all(pop0, ev, zg, opts, inj, N_inj, 5., npx, **hl)
+    same_class(lle, golden_like2[f"{name}_h{h}_lle"], 1e-10)
+    same_class([lnum, lnexp, lh], golden_like2[f"{name}_h{h}_tot"], 1e-10)
+
+
+def test_selection_bpl_mg(golden_like2, golden_in1d):
+  _, _, inj, N_inj = _inputs(golden_in1d, False)
+  pop0 = orc.make_pop(orc.make_cosmo("mg_flrw", H0=70., Om0=0.25, z_max=5.), orc.make_mass("bpl"),
+                      orc.make_rate("trunc_madau_dickinson", zmax=2.0))
+  got = [orc.N_exp(orc.pop_update(pop0, **hl), inj, N_inj, 5.)[0] for hl in SEL_BPL_MG_HYPERS]
+  close(got, golden_like2["sel_bpl_mg_nexp"], rtol=1e-11)
 
 
 def test_not_scale_free_and_neff_gate(golden_like, golden_in1d):
