@@ -279,12 +279,22 @@ static int prepare(chb_handle* h) {
   if (!h->dirty) return CHB_OK;
   const int64_t Nev = h->Nev, Ns = h->Ns, P = h->P;
   const size_t n = (size_t)Nev * Ns;
-  const bool bucket = h->have_pixels && !h->h_pe_pix.empty();
+  const int kind = h->cfg.kind_p_gw;
+  // 1-D kinds (both arithmetic modes): every per-event reduction is order-independent, so the samples of every event
+  // are sorted by dL.  z_from_dGW is monotone in dL, hence the reweighted z's come out sorted for every hyper-point and
+  // the windowed KDEs (kde_win.cuh, kde_win64.cuh) only visit the grid points near each chunk of samples.
+  h->sorted = (kind == CHB_PGW_1D || kind == CHB_PGW_APPROX);
+  const bool bucket = !h->sorted && h->have_pixels && !h->h_pe_pix.empty();
+  const bool sky = !h->h_ra.empty();
+  std::vector<double> t1, t2, t3, t4, t5, t6;
+  const double *p1 = h->h_m1.data(), *p2 = h->h_m2.data(), *p3 = h->h_dL.data(), *p4 = h->h_prior.data();
+  const double *p5 = sky ? h->h_ra.data() : nullptr, *p6 = sky ? h->h_dec.data() : nullptr;
+  if (bucket || h->sorted) {
+    t1.resize(n); t2.resize(n); t3.resize(n); t4.resize(n);
+    if (sky) { t5.resize(n); t6.resize(n); }
+  }
   if (bucket) {
     std::vector<int> off((size_t)Nev * (P + 2));
-    std::vector<double> t1(n), t2(n), t3(n), t4(n), t5, t6;
-    const bool sky = !h->h_ra.empty();
-    if (sky) { t5.resize(n); t6.resize(n); }
     std::vector<int> slot(Ns), cnt(P + 2);
     for (int64_t e = 0; e < Nev; ++e) {
       std::unordered_map<int64_t, int> map;
@@ -303,49 +313,42 @@ static int prepare(chb_handle* h) {
       std::vector<int> cur(cnt.begin(), cnt.end() - 1);
       for (int64_t j = 0; j < Ns; ++j) {
         size_t d = (size_t)e * Ns + cur[slot[j]]++, s = (size_t)e * Ns + j;
-        t1[d] = h->h_m1[s]; t2[d] = h->h_m2[s]; t3[d] = h->h_dL[s]; t4[d] = h->h_prior[s];
-        if (sky) { t5[d] = h->h_ra[s]; t6[d] = h->h_dec[s]; }
+        t1[d] = p1[s]; t2[d] = p2[s]; t3[d] = p3[s]; t4[d] = p4[s];
+        if (sky) { t5[d] = p5[s]; t6[d] = p6[s]; }
       }
     }
-    CU(h->m1d.upload(t1.data(), n), "upload m1det"); CU(h->m2d.upload(t2.data(), n), "upload m2det");
-    CU(h->dL.upload(t3.data(), n), "upload dL"); CU(h->prior.upload(t4.data(), n), "upload pe_prior");
-    if (sky) { CU(h->ra.upload(t5.data(), n), "upload ra"); CU(h->dec.upload(t6.data(), n), "upload dec"); }
     CU(h->pix_off.upload(off.data(), off.size()), "upload pixel offsets");
-  } else {
-    CU(h->m1d.upload(h->h_m1.data(), n), "upload m1det"); CU(h->m2d.upload(h->h_m2.data(), n), "upload m2det");
-    CU(h->dL.upload(h->h_dL.data(), n), "upload dL"); CU(h->prior.upload(h->h_prior.data(), n), "upload pe_prior");
-    if (!h->h_ra.empty()) { CU(h->ra.upload(h->h_ra.data(), n), "upload ra"); CU(h->dec.upload(h->h_dec.data(), n), "upload dec"); }
-  }
-  if (h->cfg.fp_mode == CHB_FP32) {
-    // single-precision copies for the fp32 reweighting path (device order = the order just uploaded)
-    std::vector<double> m1(n), m2(n), dl(n), pr(n);
-    CU(cudaMemcpy(m1.data(), h->m1d.p, n * sizeof(double), cudaMemcpyDeviceToHost), "D2H m1det");
-    CU(cudaMemcpy(m2.data(), h->m2d.p, n * sizeof(double), cudaMemcpyDeviceToHost), "D2H m2det");
-    CU(cudaMemcpy(dl.data(), h->dL.p, n * sizeof(double), cudaMemcpyDeviceToHost), "D2H dL");
-    CU(cudaMemcpy(pr.data(), h->prior.p, n * sizeof(double), cudaMemcpyDeviceToHost), "D2H pe_prior");
-    std::vector<float4> s4(n);
-    std::vector<float2> l2(n);
-    // 1-D KDE kinds: every per-event reduction is order-independent, so the packed copy is sorted by dL
-    // within each event.  z_from_dGW is monotone in dL, hence the reweighted z's come out sorted for every
-    // hyper-point and the windowed KDE only visits the grid points near each chunk of samples.
-    h->sorted = (h->cfg.kind_p_gw == CHB_PGW_1D || h->cfg.kind_p_gw == CHB_PGW_APPROX);
-    std::vector<int> perm(h->sorted ? Ns : 0);
+  } else if (h->sorted) {
+    std::vector<int> perm(Ns);
     for (int64_t e = 0; e < Nev; ++e) {
       const size_t o = (size_t)e * Ns;
-      if (h->sorted) {
-        for (int64_t j = 0; j < Ns; ++j) perm[j] = (int)j;
-        const double* key = dl.data() + o;
-        std::sort(perm.begin(), perm.end(), [key](int x, int y) { return key[x] < key[y] || (key[x] == key[y] && x < y); });
-      }
+      for (int64_t j = 0; j < Ns; ++j) perm[j] = (int)j;
+      const double* key = p3 + o;
+      std::sort(perm.begin(), perm.end(), [key](int x, int y) { return key[x] < key[y] || (key[x] == key[y] && x < y); });
       for (int64_t j = 0; j < Ns; ++j) {
-        const size_t i = o + (h->sorted ? perm[j] : j);
-        s4[o + j] = make_float4((float)dl[i], (float)m1[i], (float)m2[i], (float)(1.0 / pr[i]));
-        l2[o + j] = make_float2((float)std::log2(m1[i]), (float)std::log2(m2[i]));
+        const size_t d = o + j, s = o + perm[j];
+        t1[d] = p1[s]; t2[d] = p2[s]; t3[d] = p3[s]; t4[d] = p4[s];
+        if (sky) { t5[d] = p5[s]; t6[d] = p6[s]; }
       }
+    }
+  }
+  if (bucket || h->sorted) { p1 = t1.data(); p2 = t2.data(); p3 = t3.data(); p4 = t4.data(); if (sky) { p5 = t5.data(); p6 = t6.data(); } }
+  if (sky) { CU(h->ra.upload(p5, n), "upload ra"); CU(h->dec.upload(p6, n), "upload dec"); }
+  if (h->cfg.fp_mode == CHB_FP32) {
+    // single-precision packed copies for the fp32 reweighting path: {dL, m1det, m2det, 1/pe_prior}, {log2 m1det, log2 m2det}
+    // (the fp64 sample arrays are not read in this mode and are not uploaded)
+    std::vector<float4> s4(n);
+    std::vector<float2> l2(n);
+    for (size_t i = 0; i < n; ++i) {
+      s4[i] = make_float4((float)p3[i], (float)p1[i], (float)p2[i], (float)(1.0 / p4[i]));
+      l2[i] = make_float2((float)std::log2(p1[i]), (float)std::log2(p2[i]));
     }
     CU(h->s4.upload(s4.data(), n), "upload packed samples");
     CU(h->l2.upload(l2.data(), n), "upload log2 masses");
-    h->m1d.release(); h->m2d.release(); h->dL.release(); h->prior.release();   // fp64 copies are not read in this mode
+    h->m1d.release(); h->m2d.release(); h->dL.release(); h->prior.release();
+  } else {
+    CU(h->m1d.upload(p1, n), "upload m1det"); CU(h->m2d.upload(p2, n), "upload m2det");
+    CU(h->dL.upload(p3, n), "upload dL"); CU(h->prior.upload(p4, n), "upload pe_prior");
   }
   h->dirty = false;
   h->cat_collapsed = false;
@@ -455,10 +458,16 @@ static int eval_impl(chb_handle* h, int64_t n_hyper, const double* d_hyper, doub
         split = h->plan_ok;
       }
       if (fused || split || fs <= fit) {
-        // z-grid terms for all (hyper-point, event, k) in one full-occupancy pass when they fit in 2 GiB
+        // z-grid terms for all (hyper-point, event, k) in one full-occupancy pass when they fit (<= 16 GiB and a
+        // quarter of the free memory; otherwise the numerator kernels evaluate them in place)
         const size_t zt_elems = (size_t)n_hyper * h->Nev * h->Nz;
         a.zterms = nullptr; a.zterms_out = nullptr; a.zterms_h0 = 0;
-        if (zt_elems * sizeof(float2) <= ((size_t)2 << 30)) {
+        bool zt_fit = zt_elems * sizeof(float2) <= ((size_t)2 << 30);
+        if (!zt_fit && zt_elems * sizeof(float2) <= ((size_t)16 << 30)) {
+          if (h->zterms.n >= zt_elems) zt_fit = true;
+          else { size_t free_b = 0, total_b = 0; cudaMemGetInfo(&free_b, &total_b); zt_fit = zt_elems * sizeof(float2) <= free_b / 4; }
+        }
+        if (zt_fit) {
           CU(h->zterms.alloc(zt_elems), "alloc z-grid terms");
           a.zterms_out = h->zterms.p;
           CU(launch_zgrid_terms(a, 0, (int)n_hyper, s), "zgrid_terms launch");

@@ -45,8 +45,8 @@ enum {
   FC_MU, FC_G_HI, FC_G_C, FC_MB, FC_NEG_ALPHA2, FC_CDL_X, FC_CDL_Y, FC_LUT_B0 /* int bits */, FC_LUT_NB /* int bits */,
   FC_Z_TOP
 };
-#define CHB_LUT_SHIFT 18      // 32 buckets per octave of dL: <= 1.4 knots per bucket, so <= 2 scan steps
-#define CHB_LUT_CAP 2048      // uint16 entries
+#define CHB_LUT_SHIFT 17      // 64 buckets per octave of dL: <= 0.7 knots per bucket at the default resolution, so <= 1 scan step
+#define CHB_LUT_CAP 4096      // uint16 entries
 
 #define CHB_PI 3.141592653589793238462643383279502884
 #define CHB_DBL_MAX 1.7976931348623157e308

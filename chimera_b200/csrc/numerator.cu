@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "models_f32.cuh"
 #include "kde_f32.cuh"
+#include "kde_win64.cuh"
 #include "stage.cuh"
 
 #define NUM_THREADS 512
@@ -279,12 +280,14 @@ numerator_kernel(const NumArgs a) {
 
     // ---- effective grid (likelihood.py:115-123 / 186-190) -----------------------------
     int G = Nz;
+    double ustep = 0.0, ulb = 0.0;       // spacing / first point of the effective grid when it is our own linspace
     if (a.kind != CHB_PGW_FULL) {
       if (a.use_cut) {
         G = Nz / 2;
         const double lb = (zmn - a.cut_grid * zstd > 0.0) ? zmn - a.cut_grid * zstd : 1.e-8;
         const double ub = zmx + a.cut_grid * zstd;
         const double step = (ub - lb) / (double)(G - 1);
+        ustep = step; ulb = lb;
         for (int i = tid; i < G; i += NUM_THREADS) eg[i] = (i == G - 1) ? ub : __dadd_rn(__dmul_rn((double)i, step), lb);
       } else {
         for (int i = tid; i < G; i += NUM_THREADS) eg[i] = zgrid[i];
@@ -332,8 +335,21 @@ numerator_kernel(const NumArgs a) {
       if (a.bw_method == CHB_BW_SCOTT) bw = pow(neff_k, -0.2) * dstd;
       else if (a.bw_method == CHB_BW_SILVERMAN) bw = pow(neff_k * 3.0 / 4.0, -0.2) * dstd;
       else bw = a.bw_value * dstd;
-      kde1d_any(fp_mode, const_cast<double*>(dx), dw, dn, a.binning ? xwb : reinterpret_cast<float2*>(zs), eg, G, bw, W,
-                a.kernel, norm, part, dens);
+      bool done = false;
+      if constexpr (!F32) {
+        // fp64 mode, unbinned Gaussian on the uniform effective grid: windowed recurrence over the (sorted) samples
+        // (kde_win64.cuh) -- 2 exp2 per 8 pairs and ~1/3 of the pairs, exact to ~1e-15; scratch: chunk tables in pgw,
+        // per-warp rows in `part` (NUM_WARPS * G doubles = its NUM_WARPS * Nz floats)
+        if (!a.binning && a.kernel == CHB_KERNEL_GAUSS && ustep > 0.0 && a.kde_win_iters > 0 && Nz >= 112 && 2 * G <= Nz) {
+          float4* summ = reinterpret_cast<float4*>(pgw);
+          int2* win = reinterpret_cast<int2*>(summ + 32);
+          done = kde1d_f64_win<NUM_WARPS>(zs, ws, Ns, G, ulb, ustep, bw, W, norm * 0.3989422804014327 / bw, summ, win, pgw + 96,
+                                          reinterpret_cast<double*>(part), dens);
+        }
+      }
+      if (!done)
+        kde1d_any(fp_mode, const_cast<double*>(dx), dw, dn, a.binning ? xwb : reinterpret_cast<float2*>(zs), eg, G, bw, W,
+                  a.kernel, norm, part, dens);
       __syncthreads();
       for (int k = tid; k < Nz; k += NUM_THREADS) pgw[k] = interp_lr(zgrid[k], eg, dens, G, 0.0, 0.0);
       __syncthreads();

@@ -32,6 +32,9 @@
 #ifndef CHB_FU_MINB
 #define CHB_FU_MINB 3             // co-resident CTAs per SM the kernel is compiled for
 #endif
+#ifndef CHB_FU_PREFETCH
+#define CHB_FU_PREFETCH 1         // 1: the next block's packed samples are requested one block ahead (two register sets);
+#endif                            // 0: every block loads its own samples (12 fewer live registers, latency left to the other warps)
 
 struct FusedPlan {                // byte offsets into dynamic shared memory
   int stage, rows, dens, bc, bs, bx, sub, summ, win, cr, red, total;
@@ -51,7 +54,7 @@ __host__ __device__ inline FusedPlan make_fused_plan(int Ns, int Nz, int B) {
   p.summ = o; o += 32 * 16;
   p.win = o; o += 32 * 8;
   p.cr = o; o += 16 * 4;
-  p.red = o; o += 64 * 8;
+  p.red = o; o += 96 * 8;
   p.total = o;
   return p;
 }
@@ -116,14 +119,13 @@ __device__ __forceinline__ FuTab make_fu_tab(const TableLayout& lay, const doubl
   return t;
 }
 
-// z_from_dGW (cosmo.py:260-264): float-bits LUT -> candidate row, two-step scan (every bucket of a monotone table
-// at 32 buckets per octave), rare longer scans in a loop; clamped ends like numpy.interp.
+// z_from_dGW (cosmo.py:260-264): float-bits LUT -> candidate row, one scan step (64 buckets per octave of dL hold at
+// most one knot of the 140-per-decade table), rare longer scans in a loop; clamped ends like numpy.interp.
 __device__ __forceinline__ float fu_z_from_dL(const FuTab& t, float dL) {
   int b = (int)(__float_as_uint(dL) >> CHB_LUT_SHIFT) - t.b0;
   b = max(0, min(b, t.nb - 1));
   int k = __ldg(t.lut + b);
   float4 e = __ldg(t.dl4 + k);
-  if (dL >= e.w && k < t.rc - 2) { ++k; e = __ldg(t.dl4 + k); }
   if (dL >= e.w && k < t.rc - 2) { ++k; e = __ldg(t.dl4 + k); }
   while (dL >= e.w && k < t.rc - 2) { ++k; e = __ldg(t.dl4 + k); }
   float z = fmaf(dL - e.x, e.z, e.y);
@@ -161,16 +163,15 @@ __device__ __forceinline__ float fu_weight(const FuTab& t, float m1, float m2, f
   i = max(0, min(i, t.rm - 2));
   // (an index that is one off at a knot extrapolates the neighbouring segment by an ulp: same value to rounding)
   const float4 e = __ldg(t.cd4 + i);
-  float cdf = fmaf(m1 - e.x, e.z, e.y);
-  cdf = (m1 >= t.cdl_x) ? t.cdl_y : cdf;
+  const float cdf = fmaf(m1 - e.x, e.z, e.y);                // (m1 <= m_high = last knot inside the support: no clamp needed)
   p2 = p2 * rcpf_(cdf);
   p2 = (p2 != p2) ? 0.f : p2;                                // 0/0 -> 0 (mass.py:340)
-  const bool in = (t.lo <= m1) && (m1 <= t.hi) && (t.lo <= m2) && (m2 <= m1) && (p1 > 0.f);   // p1 == 0: never 0 * inf
+  const bool in = (m1 <= t.hi) && (t.lo <= m2) && (m2 <= m1) && (p1 > 0.f);   // (lo <= m2 <= m1 implies lo <= m1); p1 == 0: never 0 * inf
   return in ? p1 * p2 * inv_prior : 0.f;
 }
 
 // One pass over the event's packed samples: {z - z0, v} pairs to the shared-memory stage (v = log2 w when `want_lw`,
-// else w), per-warp statistics {sum w, sum w^2, sum dz, sum dz^2, min dz, max dz} to red[warp*6..] (+ z0 in red[63]), and
+// else w), per-warp statistics {sum w, sum w^2, sum dz, sum dz^2, min dz, max dz} to red[warp*6..] (+ z0 in red[95]), and
 // per 64-sample block {min dz, max dz, max log2 w, dz of that sample} over the samples with w > 0.  Static round-robin
 // of blocks over the warps: bit-reproducible.  NOT inlined: the loop gets the kernel's whole register budget to itself
 // (the unit-level state of the caller is saved around the call once per unit instead of spilling inside the loop).
@@ -187,17 +188,15 @@ __device__ __noinline__ void fu_reweight(const double* __restrict__ f32blk, int 
   // variance does not cancel and the scaled coordinates of the pair sums keep ~1e-6 absolute accuracy
   const float z0 = fu_z_from_dL(t, __ldg(&s4[Ns / 2].x));
   float fa = 0.f, fb = 0.f, fcs = 0.f, fd = 0.f, mn = INFINITY, mx = -INFINITY;
-  int cb = warp * FU_SUB;
-  float4 sa, sb, ll, nsa, nsb, nll;
-  if (cb < Ns) {
-    const int j = min(cb + 2 * lane, Ns - 2);                  // tail lanes recompute the last pair, never stored
-    sa = __ldg(s4 + j); sb = __ldg(s4 + j + 1); ll = __ldg(reinterpret_cast<const float4*>(l2 + j));
-  }
-  while (cb < Ns) {
+  // One 64-sample block: `sa, sb, ll` hold the block's packed samples (requested one block earlier), the NEXT block
+  // of this warp is requested into `na, nb, nl` before this one is evaluated (L2 latency behind ~300 instructions).
+  // The loop below alternates two register sets, so no block is ever copied between registers.
+  auto block = [&](int cb, const float4& sa, const float4& sb, const float4& ll, float4& na, float4& nb, float4& nl) {
     const int nbase = cb + FU_NW * FU_SUB;
-    if (nbase < Ns) {                                          // request the next block before evaluating this one
-      const int j = min(nbase + 2 * lane, Ns - 2);
-      nsa = __ldg(s4 + j); nsb = __ldg(s4 + j + 1); nll = __ldg(reinterpret_cast<const float4*>(l2 + j));
+    if (CHB_FU_PREFETCH && nbase < Ns) {
+      // (streamed once per unit: ld.global.cg keeps them out of L1, which then holds only the table rows in use)
+      const int j = min(nbase + 2 * lane, Ns - 2);             // tail lanes recompute the last pair, never stored
+      na = __ldcg(s4 + j); nb = __ldcg(s4 + j + 1); nl = __ldcg(reinterpret_cast<const float4*>(l2 + j));
     }
     const bool valid = cb + 2 * lane < Ns;
     const float za = fu_z_from_dL(t, sa.x), zb = fu_z_from_dL(t, sb.x);
@@ -205,8 +204,8 @@ __device__ __noinline__ void fu_reweight(const double* __restrict__ f32blk, int 
     const float ra = rcpf_(opa), rb = rcpf_(opb), lza = lg2f_(opa), lzb = lg2f_(opb);
     const float m1a = sa.y * ra, m2a = sa.z * ra, m1b = sb.y * rb, m2b = sb.z * rb;
     float wa, wb;
-    const bool taper = (MASS != CHB_MASS_TPL) &&
-                       (!(m2a - t.lo > t.dm) || !(m1a - t.lo > t.dm) || !(m2b - t.lo > t.dm) || !(m1b - t.lo > t.dm));
+    // (m2 <= m1 inside the support, so the taper test on m2 covers m1 whenever the weight is not already zero)
+    const bool taper = (MASS != CHB_MASS_TPL) && (!(m2a - t.lo > t.dm) || !(m2b - t.lo > t.dm));
     if (MASS != CHB_MASS_TPL && __any_sync(0xffffffffu, taper)) {
       wa = fu_weight<MASS, true>(t, m1a, m2a, ll.x - lza, ll.y - lza, sa.w);
       wb = fu_weight<MASS, true>(t, m1b, m2b, ll.z - lzb, ll.w - lzb, sb.w);
@@ -220,22 +219,46 @@ __device__ __noinline__ void fu_reweight(const double* __restrict__ f32blk, int 
       mn = fminf(mn, fminf(dza, dzb)); mx = fmaxf(mx, fmaxf(dza, dzb));
     }
     if (want_lw) {
-      const bool pa = valid && wa > 0.f, pb = valid && wb > 0.f;          // zero / NaN weights add exactly 0
-      const float lwa = pa ? lg2f_(wa) : -INFINITY, lwb = pb ? lg2f_(wb) : -INFINITY;
+      // log2 w: lg2(0) = -inf natively (a zero weight adds exactly 0); NaN weights are forced to -inf as well
+      float lwa = lg2f_(wa), lwb = lg2f_(wb);
+      lwa = (valid && wa > 0.f) ? lwa : -INFINITY; lwb = (valid && wb > 0.f) ? lwb : -INFINITY;
       if (valid) stage[(cb >> 1) + lane] = make_float4(dza, dzb, lwa, lwb);
-      const float lo = warp_min_f32(fminf(pa ? dza : INFINITY, pb ? dzb : INFINITY));
-      const float hi = warp_max_f32(fmaxf(pa ? dza : -INFINITY, pb ? dzb : -INFINITY));
+      // block summary over ALL its samples (a superset of the weighted ones: still a valid hull for the windows)
+      const float lo = warp_min_f32(valid ? fminf(dza, dzb) : INFINITY);
+      const float hi = warp_max_f32(valid ? fmaxf(dza, dzb) : -INFINITY);
       const float lm = fmaxf(lwa, lwb), xm = (lwa >= lwb) ? dza : dzb;
       const float lmw = warp_max_f32(lm);
-      const unsigned pick = __ballot_sync(0xffffffffu, lm == lmw && lm > -INFINITY);
-      const float xmw = __shfl_sync(0xffffffffu, xm, pick ? (__ffs(pick) - 1) : 0);
-      if (lane == 0) sub[cb / FU_SUB] = make_float4(lo, hi, pick ? lmw : -INFINITY, xmw);
+      const unsigned pick = __ballot_sync(0xffffffffu, lm == lmw);
+      const float xmw = __shfl_sync(0xffffffffu, xm, __ffs(pick) - 1);
+      if (lane == 0) sub[cb / FU_SUB] = make_float4(lo, hi, lmw, xmw);
     } else if (valid) {
       stage[(cb >> 1) + lane] = make_float4(dza, dzb, wa, wb);
     }
-    cb = nbase;
-    sa = nsa; sb = nsb; ll = nll;
+  };
+  int cb = warp * FU_SUB;
+  float4 a0, a1, a2, b0, b1, b2;
+  if (cb < Ns) {
+    const int j = min(cb + 2 * lane, Ns - 2);
+    a0 = __ldcg(s4 + j); a1 = __ldcg(s4 + j + 1); a2 = __ldcg(reinterpret_cast<const float4*>(l2 + j));
   }
+#if CHB_FU_PREFETCH
+  while (cb < Ns) {
+    block(cb, a0, a1, a2, b0, b1, b2);
+    cb += FU_NW * FU_SUB;
+    if (cb >= Ns) break;
+    block(cb, b0, b1, b2, a0, a1, a2);
+    cb += FU_NW * FU_SUB;
+  }
+#else
+  while (cb < Ns) {
+    block(cb, a0, a1, a2, b0, b1, b2);
+    cb += FU_NW * FU_SUB;
+    if (cb < Ns) {
+      const int j = min(cb + 2 * lane, Ns - 2);
+      a0 = __ldcg(s4 + j); a1 = __ldcg(s4 + j + 1); a2 = __ldcg(reinterpret_cast<const float4*>(l2 + j));
+    }
+  }
+#endif
   // warp-level reduction; fp64 from here on
   double da = (double)fa, db = (double)fb, dc = (double)fcs, dd = (double)fd;
 #pragma unroll
@@ -249,7 +272,7 @@ __device__ __noinline__ void fu_reweight(const double* __restrict__ f32blk, int 
   if (lane == 0) {
     red[warp * 6 + 0] = da; red[warp * 6 + 1] = db; red[warp * 6 + 2] = dc; red[warp * 6 + 3] = dd;
     red[warp * 6 + 4] = (double)mn; red[warp * 6 + 5] = (double)mx;
-    if (warp == 0) red[63] = (double)z0;
+    if (warp == 0) red[95] = (double)z0;
   }
 }
 
@@ -394,7 +417,7 @@ numerator_fused_kernel(const NumArgs a) {
       st.a += red[i * 6 + 0]; st.b += red[i * 6 + 1]; st.c += red[i * 6 + 2]; st.d += red[i * 6 + 3];
       st.mn = fminf(st.mn, (float)red[i * 6 + 4]); st.mx = fmaxf(st.mx, (float)red[i * 6 + 5]);
     }
-    const float z0 = (float)red[63];
+    const float z0 = (float)red[95];
     const double s1 = st.a, s2 = st.b;
     const double zmn = (double)z0 + (double)st.mn, zmx = (double)z0 + (double)st.mx;
     const double dzmean = st.c / Ns;

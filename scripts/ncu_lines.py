@@ -76,3 +76,15 @@ if main:
   print(f"\n== by enclosing line of {main} ==")
   for l, (s, ex) in sorted(per_main.items(), key=lambda kv: -kv[1][0])[:topn]:
     print(f"{100*s/tot:5.1f}%  {s:7d} smp  {ex:10d} inst  {main}:{l}")
+
+# optional region totals: NCU_REGIONS="name:lo-hi,name:lo-hi" over the enclosing lines of the main file
+reg = os.environ.get("NCU_REGIONS")
+if main and reg:
+  print(f"\n== regions of {main} (enclosing lines) ==")
+  texe = sum(ex for _, ex in per_main.values())
+  for item in reg.split(","):
+    nm, rng = item.split(":")
+    lo_, hi_ = (int(x) for x in rng.split("-"))
+    s_ = sum(v[0] for l, v in per_main.items() if lo_ <= l <= hi_)
+    e_ = sum(v[1] for l, v in per_main.items() if lo_ <= l <= hi_)
+    print(f"{nm:>16}: {100*s_/tot:5.1f}% samples  {100*e_/texe:5.1f}% instructions  ({e_} warp inst)")

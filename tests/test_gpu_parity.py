@@ -320,9 +320,11 @@ def test_compute_z_grids(cb, golden_setup):
   close(cb.compute_z_grids(mg, th, {"H0": [50., 90.], "Xi0": [0.5, 2.], "n": [1., 3.]}, 40), g["zgrid_mg"], 1e-11)
 
 
+@pytest.mark.parametrize("fp_mode,tol", [("fp32", 2e-4), ("fp64", 1e-9)])
 @pytest.mark.parametrize("kind,zmax", [(None, 0.45), (None, 5.0), ("approximate", 0.6)])
-def test_windowed_kde_bulk_and_tails(cb, kind, zmax):
-  """fp32 mode with enough samples for the windowed recurrence (kde_win.cuh).  A truncated rate model
+def test_windowed_kde_bulk_and_tails(cb, kind, zmax, fp_mode, tol):
+  """Both modes with enough samples for the windowed recurrence (kde_win.cuh; kde_win64.cuh in fp64 mode, where the
+  recurrence and the 2^-64 windows must keep the 1e-9 agreement of the exhaustive fp64 pair sums).  A truncated rate model
   (psi = 0 above zmax, rate.py:118-129) makes the likelihood of every event beyond zmax an integral over
   the FAR LOWER TAIL of its KDE, so this checks that the windows keep the tails exact (fp64 oracle)."""
   from oracle import chimera_oracle as orc
@@ -337,7 +339,7 @@ def test_windowed_kde_bulk_and_tails(cb, kind, zmax):
   th = cb.theta_pe_det(**kw)
   sel = cb.selection_function(cb.theta_inj_det(**inj), N_inj, 5.)
   pop = cb.population(cb.cosmo.flrw(z_max=5.), cb.mass.plp(), cb.rate.trunc_madau_dickinson(zmax=zmax), gal_cat=gcat)
-  like = cb.hyperlikelihood(th, zg, pop, sel, kind_p_gw3d=kind, kernel="gauss", binning=False, fp_mode="fp32")
+  like = cb.hyperlikelihood(th, zg, pop, sel, kind_p_gw3d=kind, kernel="gauss", binning=False, fp_mode=fp_mode)
   pop0 = orc.make_pop(orc.make_cosmo("flrw", z_max=5.), orc.make_mass("plp"),
                       orc.make_rate("trunc_madau_dickinson", zmax=zmax), catalog=cat)
   opts = orc.make_opts(kind, "gauss", None, 2.0, False, 200, 2.0)
@@ -350,7 +352,7 @@ def test_windowed_kde_bulk_and_tails(cb, kind, zmax):
     assert np.array_equal(fin, np.isfinite(lle[h]) & (np.abs(lle[h]) < 1e300))
     # |d log L| relative to max(|log L|, 1): log-likelihoods cross zero, likelihoods carry the relative error
     err = np.abs(lle[h][fin] - ref[fin]) / np.maximum(np.abs(ref[fin]), 1.0)
-    assert err.max() < 2e-4, (h0, err.max(), lle[h][fin][np.argmax(err)], ref[fin][np.argmax(err)])
+    assert err.max() < tol, (h0, err.max(), lle[h][fin][np.argmax(err)], ref[fin][np.argmax(err)])
     n_tail += int(np.sum(ref[fin] < -30.))
   if zmax < 1.0:
     assert n_tail > 0      # the case really contains tail-dominated events

@@ -27,11 +27,8 @@ def _err(x, r):
 def c3(cb):
   """C3 at full size: 1000 events x 5000 samples, pixelated catalogue ('approximate'), Gaussian KDE unbinned."""
   import bench
-
-  class A:
-    nev, ns, ninj, nz, hyper_side = 1000, 5000, 200_000, 300, 16
-  w = bench.build_workload(A, 0)
-  like = bench.build_likelihood(w, "fp32", False)
+  w = bench.build_workload("C3", ninj=200_000)      # GPU pixelisation + precompute_p_cat from 1.6e6 galaxies (spiky rows)
+  like = bench.build_likelihood(w, "fp32")
   return w, like
 
 
@@ -42,13 +39,13 @@ def test_c3_fp32_vs_fp64_and_oracle(cb, c3):
   idx = np.linspace(0, 255, 6).astype(int)
   hy = {k: v[idx] for k, v in w["hyper"].items()}
   l32 = like.compute_all(**hy)
-  like64 = bench.build_likelihood(w, "fp64", False)
+  like64 = bench.build_likelihood(w, "fp64")
   l64 = like64.compute_all(**hy)
   assert _err(l32[0], l64[0]) < 1e-5            # per-event log-likelihoods, fp32 mode vs fp64 mode (budget 1e-3)
   np.testing.assert_allclose(l32[3], l64[3], rtol=1e-6)    # total log hyper-likelihood
   # oracle on the first 12 events, two hyper-points (fp64 mode 1e-9, fp32 mode 1e-5)
   ev = {k: np.asarray(w["ev"][k])[:12] for k in ("m1det", "m2det", "dL", "pe_prior", "pixels_opt_nsides", "gw_loc2d_pdf")}
-  cat = dict(p_cat=w["p_cat"][:12], P_compl=w["P_compl"][:12], z_range=w["z_range"])
+  cat = dict(p_cat=w["p_cat"][:12], P_compl=w["P_compl"][:12][:, None, :], z_range=w["z_range"])
   pop0 = orc.make_pop(orc.make_cosmo("flrw", H0=70., Om0=0.25, z_max=5.), orc.make_mass("plp"),
                       orc.make_rate("madau_dickinson"), catalog=cat)
   opts = orc.make_opts("approximate", "gauss", None, 2.0, False, 200, 2.0)
@@ -79,13 +76,13 @@ def test_c3_invariances(cb, c3):
   c = 7.25
   ev["pe_prior"] = ev["pe_prior"] * c
   w2 = dict(w, ev=ev)
-  like2 = bench.build_likelihood(w2, "fp32", False)
+  like2 = bench.build_likelihood(w2, "fp32")
   out2 = like2.compute_all(**hy)[0]
   assert _err(out2 + np.log(c), base) < 2e-6
   # (3) sharding: two handles with half of the events each reproduce the per-event values bit for bit
   half = {k: (np.asarray(v)[:500] if np.ndim(v) and np.shape(v)[0] == 1000 else v) for k, v in w["ev"].items()}
   w3 = dict(w, ev=half, zg=w["zg"][:500], p_cat=w["p_cat"][:500], P_compl=w["P_compl"][:500])
-  out3 = bench.build_likelihood(w3, "fp32", False).compute_all(**hy)[0]
+  out3 = bench.build_likelihood(w3, "fp32").compute_all(**hy)[0]
   np.testing.assert_array_equal(out3, base[:, :500])
 
 
