@@ -405,8 +405,14 @@ def kde_roofline(w, tm, fp_mode, mufu_peak, clocks, binning=None, nev_local=None
     per_unit = float(np.mean(w["ev"]["neff_pixels"])) * G * (200 if binned else c["ns"])    # x pixels; bins per pixel when binned
     what = f"neff_pixels*G*{'B' if binned else 'Ns'} kernel evaluations per unit (Epanechnikov: no exp; counted as pair evaluations)"
   elif c["kind"] == "full":
-    per_unit = float(np.mean(w["ev"]["neff_pixels"])) * c["nz"] * c["ns"]                  # upper bound: n_z_eff <= Nz
-    what = "neff_pixels*n_z_eff*Ns exps per unit, n_z_eff <= Nz used as the bound"
+    # n_z_eff = grid points inside [min z - c std, max z + c std] (likelihood.py:225), evaluated at the fiducial cosmology
+    from chimera_b200 import synth
+    z = synth._FlatLCDM().z_of_dL(w["ev"]["dL"])
+    lo, hi = z.min(axis=1) - 2.0 * z.std(axis=1), z.max(axis=1) + 2.0 * z.std(axis=1)
+    nzeff = np.sum((w["zg"] >= lo[:, None]) & (w["zg"] <= hi[:, None]), axis=1)
+    per_unit = float(np.mean(w["ev"]["neff_pixels"] * nzeff)) * c["ns"]
+    what = (f"neff_pixels*n_z_eff*Ns exps per unit (mean neff_pixels {float(np.mean(w['ev']['neff_pixels'])):.1f}, mean n_z_eff "
+            f"{float(np.mean(nzeff)):.1f} of {c['nz']} at the fiducial cosmology)")
   else:
     per_unit = float(G) * n_data
     what = f"G*{'B' if binned else 'Ns'} = {G}*{n_data} {'exps' if c['kernel'] == 'gauss' else 'pair evaluations'} per unit"
@@ -709,7 +715,7 @@ def _multi_gpu_subs(args, rank, world, local_rank, configs, mufu_peak, subs=None
         rec = {"scaling": "weak", "events_per_gpu": w["ev"]["dL"].shape[0], "ms_per_step": tm["ms_per_step"],
                "value": units / (tm["ms_per_step"] * 1e-3), "unit": UNIT, "kernel_ms": tm["kernel_ms"]}
       elif s == "C5":
-        if world < 8:
+        if world < 8 and args.sub == "auto":
           continue
         w = build_workload("C5", seed_rank=0)
         rec = {"workload": CONFIGS["C5"]["workload"], "unit": UNIT}
