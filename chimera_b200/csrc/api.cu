@@ -68,6 +68,7 @@ struct chb_handle {
   int plan_per1 = 0, plan_per2 = 0;
   bool plan_ok = false;
   int fused_per = -1;                      // co-resident CTAs per SM of numerator_fused_kernel for the current shapes
+  int marg_per = -1;                       // likewise numerator_marg_kernel ('marginalized' + binning)
   // tuning / diagnostic options (chb_set_option); they never change what is computed, only how
   int opt_fused = 1;                       // 1-D kinds, fp32: one fused kernel (numerator_fused.cu); 0: round-1 split kernels
   int opt_split = 1;                       // round-1 path: split MODE 1 -> stage -> MODE 2 (0: one MODE 0 kernel)
@@ -199,7 +200,7 @@ int chb_set_events(chb_handle* h, int64_t Nev, int64_t Ns, int64_t Nz, const dou
   if (ra && dec) { h->h_ra.assign(ra, ra + n); h->h_dec.assign(dec, dec + n); } else { h->h_ra.clear(); h->h_dec.clear(); }
   CU(h->zgrids.upload(z_grids, (size_t)Nev * Nz), "upload z_grids");
   h->have_events = true; h->have_pixels = false; h->have_catalog = false; h->dirty = true;
-  h->plan_nh = -1; h->fused_per = -1;
+  h->plan_nh = -1; h->fused_per = -1; h->marg_per = -1;
   return CHB_OK;
 }
 
@@ -230,7 +231,7 @@ int chb_set_pixels(chb_handle* h, int64_t P, const int64_t* pixels_opt_nsides, c
   }
   CU(h->neff_pix.upload(neff.data(), neff.size()), "upload neff_pixels");
   h->have_pixels = true; h->dirty = true;
-  h->plan_nh = -1; h->fused_per = -1;
+  h->plan_nh = -1; h->fused_per = -1; h->marg_per = -1;
   return CHB_OK;
 }
 
@@ -427,11 +428,19 @@ static int eval_impl(chb_handle* h, int64_t n_hyper, const double* d_hyper, doub
         cudaGetLastError();
       }
       if (fused && h->fused_per < 1) fused = false;
+      // (1b) 'marginalized' + binning (the reference's default options): fused kernel, warp per pixel
+      const size_t fm = numerator_marg_smem_bytes(a);
+      bool marg = !fused && h->opt_fused && numerator_marg_supported(a) && fm <= fit;
+      if (marg && h->marg_per < 0) {
+        h->marg_per = (numerator_marg_configure(optin) == cudaSuccess) ? numerator_marg_ctas_per_sm(fm) : 0;
+        cudaGetLastError();
+      }
+      if (marg && h->marg_per < 1) marg = false;
       // (2) other kinds (and the A/B switch): split form -- reweighting kernel -> stage buffers in global memory ->
       // KDE/z-integral kernel; fused MODE 0 kernel for odd Ns or when there is no memory for the stage.
       size_t fs = numerator_f32_smem_bytes(a, 0);
       const size_t fs1 = numerator_f32_smem_bytes(a, 1), fs2 = numerator_f32_smem_bytes(a, 2);
-      bool split = !fused && h->opt_split && (h->Ns % 2 == 0) && fs2 <= fit && fs1 <= fit;
+      bool split = !fused && !marg && h->opt_split && (h->Ns % 2 == 0) && fs2 <= fit && fs1 <= fit;
       int64_t nb = n_hyper;                        // hyper-points per batch of the split form
       if (split) {
         // the plan (batch size, stage buffers, occupancy) is cached per n_hyper and reset by chb_set_* / chb_set_option:
@@ -457,7 +466,7 @@ static int eval_impl(chb_handle* h, int64_t n_hyper, const double* d_hyper, doub
         nb = h->plan_nb;
         split = h->plan_ok;
       }
-      if (fused || split || fs <= fit) {
+      if (fused || marg || split || fs <= fit) {
         // z-grid terms for all (hyper-point, event, k) in one full-occupancy pass when they fit (<= 16 GiB and a
         // quarter of the free memory; otherwise the numerator kernels evaluate them in place)
         const size_t zt_elems = (size_t)n_hyper * h->Nev * h->Nz;
@@ -479,6 +488,11 @@ static int eval_impl(chb_handle* h, int64_t n_hyper, const double* d_hyper, doub
           const int grid = (int)std::min<long long>(units, (long long)h->sm_count * h->fused_per);
           h->num_grid = grid; h->num_smem = ff;
           CU(launch_numerator_fused(a, grid, ff, s), "numerator_fused launch");
+          fast = true;
+        } else if (marg) {
+          const int grid = (int)std::min<long long>(units, (long long)h->sm_count * h->marg_per);
+          h->num_grid = grid; h->num_smem = fm;
+          CU(launch_numerator_marg(a, grid, fm, s), "numerator_marg launch");
           fast = true;
         } else if (split) {
           const int per1 = h->plan_per1, per2 = h->plan_per2;
@@ -571,7 +585,7 @@ int chb_set_option(chb_handle* h, const char* name, double value) {
   else if (n == "bin_runs") h->opt_bin_runs = value != 0.0;
   else if (n == "stage_gb") { if (!(value > 0.0)) return fail(h, CHB_ERR_INVALID, "stage_gb must be positive"); h->opt_stage_gb = value; }
   else return fail(h, CHB_ERR_INVALID, "unknown option '" + n + "'");
-  h->plan_nh = -1; h->fused_per = -1;
+  h->plan_nh = -1; h->fused_per = -1; h->marg_per = -1;
   return CHB_OK;
 }
 

@@ -87,6 +87,11 @@ bool numerator_fused_supported(const NumArgs& a);
 cudaError_t numerator_fused_configure(size_t smem);
 int numerator_fused_ctas_per_sm(size_t smem);
 cudaError_t launch_numerator_fused(const NumArgs& a, int grid, size_t smem, cudaStream_t s);
+size_t numerator_marg_smem_bytes(const NumArgs& a);
+bool numerator_marg_supported(const NumArgs& a);
+cudaError_t numerator_marg_configure(size_t optin);
+int numerator_marg_ctas_per_sm(size_t smem);
+cudaError_t launch_numerator_marg(const NumArgs& a, int grid, size_t smem, cudaStream_t s);
 cudaError_t launch_zgrid_terms(const NumArgs& a, int h0, int nh, cudaStream_t s);
 cudaError_t launch_catalog_collapse(int Nev, int P, int Nz, const double* p_cat, const double* gw_pdf, const int* neff_pix,
                                    double* catA, double* catB, cudaStream_t s);

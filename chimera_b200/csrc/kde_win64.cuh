@@ -13,6 +13,30 @@
 #pragma once
 #include "kde_win.cuh"
 
+// 2^x for finite x or x = -inf, |error| < 2e-16 relative: n = rint(x), f = x - n in [-1/2, 1/2], degree-12 Taylor
+// polynomial of 2^f = e^(f ln 2) (remainder (ln2/2)^13/13! = 1.7e-16), exponent added to the result's bits.  No special
+// cases beyond underflow to 0 (x < -1021) -- what the pair sums need; ~20 instructions instead of ~50 for exp2().
+__device__ __forceinline__ double exp2_fast(double x) {
+  if (!(x > -1021.0)) return 0.0;
+  x = fmin(x, 1023.0);
+  const double n = rint(x), f = x - n;
+  double p = 2.5678435993488196e-11;                       // c_k = ln2^k / k!, k = 12 .. 0 (Horner)
+  p = fma(p, f, 4.4455382718708101e-10);
+  p = fma(p, f, 7.0549116208011209e-09);
+  p = fma(p, f, 1.0178086009239696e-07);
+  p = fma(p, f, 1.3215486790144305e-06);
+  p = fma(p, f, 1.5252733804059838e-05);
+  p = fma(p, f, 1.5403530393381606e-04);
+  p = fma(p, f, 1.3333558146428441e-03);
+  p = fma(p, f, 9.6181291076284769e-03);
+  p = fma(p, f, 5.5504108664821576e-02);
+  p = fma(p, f, 2.4022650695910069e-01);
+  p = fma(p, f, 6.9314718055994529e-01);
+  p = fma(p, f, 1.0);
+  const int hi = __double2hiint(p) + ((int)n << 20);       // p in [0.70, 1.42]: adding n to the exponent cannot wrap for |n| <= 1023
+  return __hiloint2double(hi, __double2loint(p));
+}
+
 #define CHB_WIN64_T2 64.0f
 #define CHB_WIN64_R 8
 #define CHB_WIN64_LPS 4
@@ -33,8 +57,8 @@ __device__ __forceinline__ void kde_win64_pass(const double* __restrict__ xs, co
   for (int r = 0; r < R; ++r) acc[r] = 0.0;
   for (int j = cb + sub; j < ce; j += S) {
     const double d = gp - xs[j];
-    const double e0 = exp2(fma(-d, d, lws[j]));                 // w' 2^-(d^2)   (lw = -inf -> 0)
-    const double q = exp2(fmin(fma(d, m2h, mh2), 900.0 / (double)R));
+    const double e0 = exp2_fast(fma(-d, d, lws[j]));            // w' 2^-(d^2)   (lw = -inf -> 0)
+    const double q = exp2_fast(fmin(fma(d, m2h, mh2), 900.0 / (double)R));
     double p = e0;
     acc[0] += p;
 #pragma unroll
@@ -68,9 +92,9 @@ __device__ __forceinline__ bool kde1d_f64_win(double* __restrict__ zs, double* _
   const double c = lb + 0.5 * step * (double)(G - 1);
   const double gfirst = (lb - c) * s, hd = step * s;
   const float h = (float)hd;
-  // windows must be much narrower than the grid, and a run must stay inside the fp64 range
-  const int wn = 2 * (int)ceilf(8.6f / h) + CHB_WIN_SPAN;
-  if (!(h > 0.f) || h > 1.8f || 10 * wn > 8 * G || n < 512 || G < 32) return false;
+  // the recurrence needs a run to stay inside the fp64 range (R h <= ~15); windows as wide as the grid are fine -- the
+  // recurrence alone is 4x fewer exps than the exhaustive sums
+  if (!(h > 0.f) || h > 1.8f || n < 512 || G < 32) return false;
   int chunk = ((n + 31) / 32 + 31) / 32 * 32;                  // <= 32 chunks, multiples of 32 samples
   chunk = max(chunk, 64);
   const int nchunks = (n + chunk - 1) / chunk;

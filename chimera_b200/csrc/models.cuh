@@ -97,6 +97,29 @@ __device__ __forceinline__ double interp_lr(double x, const double* __restrict__
   return f;
 }
 
+// The same interval as `upper_index` (i - 1 = last knot <= x), found without a binary search:
+//  * dL table: the float-bits LUT of the fp32 block gives the last knot at or below the lower edge of the bucket of
+//    float_round_down(x) <= x, then a forward scan in the fp64 table (<= 1 step at the default resolution);
+//  * log-spaced table (m_grid): direct index from log10(x), then a fix-up scan in either direction.
+// Exactly the interval of the binary search, hence bit-identical interpolants.
+__device__ __forceinline__ int upper_index_lut(const double* __restrict__ xp, int n, double x,
+                                               const unsigned short* __restrict__ lut, int b0, int nb) {
+  if (nb <= 0 || !(x > 0.0)) return upper_index(xp, n, x);
+  int b = (int)(__float_as_uint(__double2float_rd(x)) >> CHB_LUT_SHIFT) - b0;
+  b = max(0, min(b, nb - 1));
+  int k = lut[b];
+  while (k < n - 2 && xp[k + 1] <= x) ++k;
+  return k + 1;
+}
+__device__ __forceinline__ int upper_index_log(const double* __restrict__ xp, int n, double x, double log10_x,
+                                               double log10_first, double inv_dlog10) {
+  int k = (int)((log10_x - log10_first) * inv_dlog10);
+  k = max(0, min(k, n - 2));
+  while (k < n - 2 && xp[k + 1] <= x) ++k;
+  while (k > 0 && xp[k] > x) --k;
+  return k + 1;
+}
+
 // ------------------------------------------------------------------------------------------
 // cosmology
 __device__ __forceinline__ double E_at_z(const double* __restrict__ P, const double* __restrict__ HC, double z) {
@@ -203,6 +226,17 @@ __device__ __forceinline__ double p_m1m2(int mass_model, const double* __restric
                                          double m1, double m2) {
   double p1 = primary_notnorm(mass_model, P, HC, m1) / HC[HC_NORM_P_M1];
   double p2 = secondary_notnorm(mass_model, P, m2, m1) / interp_clamped(m1, mg, cdf, rm);
+  if (isnan(p2)) p2 = 0.0;
+  return p1 * p2;
+}
+
+// same with the log-spaced index (no binary search over m_grid); bit-identical to p_m1m2
+__device__ __forceinline__ double p_m1m2_logidx(int mass_model, const double* __restrict__ P, const double* __restrict__ HC,
+                                                const double* __restrict__ mg, const double* __restrict__ cdf, int rm,
+                                                double m1, double m2) {
+  double p1 = primary_notnorm(mass_model, P, HC, m1) / HC[HC_NORM_P_M1];
+  const int i = upper_index_log(mg, rm, m1, log10(m1), HC[HC_LOG10_MLOW], 1.0 / HC[HC_DLOG10_M]);
+  double p2 = secondary_notnorm(mass_model, P, m2, m1) / interp_at(m1, mg, cdf, rm, i);
   if (isnan(p2)) p2 = 0.0;
   return p1 * p2;
 }

@@ -241,12 +241,16 @@ numerator_kernel(const NumArgs a) {
         zmn = fmin(zmn, z); zmx = fmax(zmx, z);
       }
     } else {
+      // table intervals without binary searches (bit-identical interpolants): float-bits LUT of the fp32 block for
+      // dL -> z (read through L1), log-spaced direct index for the conditional cdf
+      const unsigned short* lut = reinterpret_cast<const unsigned short*>(a.tabs + (size_t)h * lay.total() + lay.off_f32() + lay.f32_lut());
+      const int lut_b0 = (int)HC[HC_LUT_B0], lut_nb = (int)HC[HC_LUT_NB];
       for (int j = tid; j < Ns; j += NUM_THREADS) {
         const double dL = __ldg(a.dL + so + j);
-        const double z = interp_clamped(dL, dLt, zg, rc);
+        const double z = interp_at(dL, dLt, zg, rc, upper_index_lut(dLt, rc, dL, lut, lut_b0, lut_nb));
         const double opz = 1.0 + z;
         const double m1 = __ldg(a.m1d + so + j) / opz, m2 = __ldg(a.m2d + so + j) / opz;
-        const double w = p_m1m2(mm, P, HC, mg, cdf, rm, m1, m2) / __ldg(a.prior + so + j);
+        const double w = p_m1m2_logidx(mm, P, HC, mg, cdf, rm, m1, m2) / __ldg(a.prior + so + j);
         zs[j] = z;
         ws[j] = w;
         s1 += w; s2 += w * w; sz += z;

@@ -48,7 +48,7 @@ __host__ __device__ inline FusedPlan make_fused_plan(int Ns, int Nz, int B) {
   p.stage = o; o += Ns * 8;                       // float4 per two samples {dz_a, dz_b, v_a, v_b}
   p.rows = o; o += FU_NW * G * 8;                 // per-warp partial rows (doubles)
   p.dens = o; o += ((G + 1) & ~1) * 8;
-  p.bc = o; o += Bp * 8;
+  p.bc = o; o += 3 * (B + 2) * 8;                 // inclusive prefix sums S0 | S1 | S2 over the bins (Epanechnikov)
   p.bs = o; o += Bp * 8;
   p.bx = o; o += Bp * 8;                          // binned data set in pair layout
   p.sub = o; o += ((Ns + FU_SUB - 1) / FU_SUB) * 16;
@@ -337,6 +337,61 @@ __device__ __noinline__ void fu_direct(const float4* __restrict__ pairs, int npa
   }
 }
 
+// ---- Epanechnikov KDE of B equally spaced bin centres by prefix sums (utils/math.py:32-46 + 52-85) -------------------
+// kde1d with the compact kernel K(u) = 3/4 (1 - u^2) [|u| <= 1] over bin centres c_b = first + b * bstep with weights
+// w_b: the bins inside the support of a grid point form a contiguous index range, so
+//     sum_b w'_b (1 - (gu - u_b)^2) = (1 - gu^2) dS0 + 2 gu dS1 - dS2,   u = (c - cmid) / bw,
+// with dS* differences of inclusive prefix sums of {w', w' u, w' u^2} (fp64; coordinates centred on the bin range and
+// scaled by 1/bw so the cancellation costs ~2 digits of 16).  O(B) to build (one warp), O(1) per grid point.
+struct EpanBins { double zlo, zhi, bstep, cmid, inv_bw, u_first, inv_du; int B; };
+__device__ __forceinline__ double epan_bin_centre(const EpanBins& eb, int i) {
+  const double e0 = __dadd_rn(__dmul_rn((double)i, eb.bstep), eb.zlo);             // linspace edges (utils/math.py:35)
+  const double e1 = (i + 1 == eb.B) ? eb.zhi : __dadd_rn(__dmul_rn((double)(i + 1), eb.bstep), eb.zlo);
+  return (e0 + e1) / 2;
+}
+__device__ __forceinline__ EpanBins make_epan_bins(double zlo, double zhi, int B, double bw) {
+  EpanBins eb;
+  eb.zlo = zlo; eb.zhi = zhi; eb.B = B; eb.bstep = (zhi - zlo) / (double)B;
+  eb.cmid = 0.5 * (zlo + zhi); eb.inv_bw = 1.0 / bw;
+  eb.u_first = (epan_bin_centre(eb, 0) - eb.cmid) * eb.inv_bw;
+  eb.inv_du = 1.0 / (eb.bstep * eb.inv_bw);
+  return eb;
+}
+// one warp: S0/S1/S2[0..B] from the bin sums (float), normalised by 1/W
+__device__ __forceinline__ void epan_bins_prefix(const EpanBins& eb, const float* __restrict__ bins, double invW,
+                                                 double* __restrict__ S0, double* __restrict__ S1, double* __restrict__ S2) {
+  const int lane = threadIdx.x & 31;
+  const int seg = (eb.B + 31) / 32, b0 = min(eb.B, lane * seg), b1 = min(eb.B, b0 + seg);
+  double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+  for (int i = b0; i < b1; ++i) {
+    const double wn = (double)bins[i] * invW, u = (epan_bin_centre(eb, i) - eb.cmid) * eb.inv_bw;
+    t0 += wn; t1 += wn * u; t2 += wn * u * u;
+  }
+  double e0 = t0, e1 = t1, e2 = t2;                           // inclusive scan of the segment totals, made exclusive below
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double y0 = __shfl_up_sync(0xffffffffu, e0, o), y1 = __shfl_up_sync(0xffffffffu, e1, o), y2 = __shfl_up_sync(0xffffffffu, e2, o);
+    if (lane >= o) { e0 += y0; e1 += y1; e2 += y2; }
+  }
+  e0 -= t0; e1 -= t1; e2 -= t2;
+  if (lane == 0) { S0[0] = 0.0; S1[0] = 0.0; S2[0] = 0.0; }
+  for (int i = b0; i < b1; ++i) {
+    const double wn = (double)bins[i] * invW, u = (epan_bin_centre(eb, i) - eb.cmid) * eb.inv_bw;
+    e0 += wn; e1 += wn * u; e2 += wn * u * u;
+    S0[i + 1] = e0; S1[i + 1] = e1; S2[i + 1] = e2;
+  }
+}
+// sum_b w'_b (1 - ((g - c_b)/bw)^2) over the bins with |g - c_b| <= bw (bins exactly on the edge contribute 0 either way)
+__device__ __forceinline__ double epan_bins_sum(const EpanBins& eb, double g, const double* __restrict__ S0,
+                                                const double* __restrict__ S1, const double* __restrict__ S2) {
+  const double gu = (g - eb.cmid) * eb.inv_bw;
+  int lo = (int)ceil((gu - 1.0 - eb.u_first) * eb.inv_du), hi = (int)floor((gu + 1.0 - eb.u_first) * eb.inv_du);
+  lo = max(lo, 0); hi = min(hi, eb.B - 1);
+  if (!(hi >= lo)) return (gu == gu) ? 0.0 : gu;              // (NaN bandwidth propagates, as in the reference)
+  const double d0 = S0[hi + 1] - S0[lo], d1 = S1[hi + 1] - S1[lo], d2 = S2[hi + 1] - S2[lo];
+  return (1.0 - gu * gu) * d0 + 2.0 * gu * d1 - d2;
+}
+
 // Windowed recurrence KDE of the staged samples (kde_win.cuh) -- NOT inlined, for the same reason as fu_reweight.
 // Merges the 64-sample block summaries into the plan's chunks (scaled units, weights normalised), then phases B and C.
 __device__ __noinline__ void fu_kde_win(const float4* __restrict__ stage, int Ns, int G, double gfirst, double hd, int R,
@@ -465,44 +520,40 @@ numerator_fused_kernel(const NumArgs a) {
       }
     } else {
       // ---- binning1d (utils/math.py:32-46) on the shared-memory stage, then the KDE of the B bin centres -------
-      const double bstep = (zmx - zmn) / (double)B;
-      for (int i = tid; i < B; i += FU_NT) {
-        const double e0 = __dadd_rn(__dmul_rn((double)i, bstep), zmn);
-        const double e1 = (i + 1 == B) ? zmx : __dadd_rn(__dmul_rn((double)(i + 1), bstep), zmn);
-        bc[i] = (e0 + e1) / 2;
-        bs[i] = 0.0;
-      }
+      float* binsf = reinterpret_cast<float*>(bs);
+      for (int i = tid; i < B; i += FU_NT) binsf[i] = 0.f;
       __syncthreads();
       {
         // the samples are sorted by dL, hence by z: a bin is a contiguous run.  Every thread walks a contiguous block
-        // of pairs, sums each run in a register and touches shared memory once per run.  Correct for any order.
+        // of pairs, sums each run in a register and touches shared memory once per run (native fp32 shared atomics).
+        // The bin index is taken in fp32 on {z - z0}: z itself is an fp32 number, so the index is as exact as its input.
         const int npairs = Ns / 2;
         const int per = (npairs + FU_NT - 1) / FU_NT;
         const int ja = min(npairs, tid * per), jb = min(npairs, ja + per);
-        const double invB = (double)B / (zmx - zmn), off = (double)z0 - zmn;
+        const float invB = (float)((double)B / (zmx - zmn)), dlo = st.mn;
         int cur = -1;
-        double run = 0.0;
+        float run = 0.f;
         for (int j = ja; j < jb; ++j) {
           const float4 v = stage[j];
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
-            const double f = floor(((double)(q ? v.y : v.x) + off) * invB);
-            if (isnan(f)) continue;
-            const int b = (int)fmin(fmax(f, 0.0), (double)(B - 1));
+            const float f = floorf(((q ? v.y : v.x) - dlo) * invB);
+            if (f != f) continue;
+            const int b = (int)fminf(fmaxf(f, 0.f), (float)(B - 1));
             if (b != cur) {
-              if (cur >= 0) atomicAdd(&bs[cur], run);
-              cur = b; run = 0.0;
+              if (cur >= 0) atomicAdd(&binsf[cur], run);
+              cur = b; run = 0.f;
             }
-            run += (double)(q ? v.w : v.z);
+            run += (q ? v.w : v.z);
           }
         }
-        if (cur >= 0) atomicAdd(&bs[cur], run);
+        if (cur >= 0) atomicAdd(&binsf[cur], run);
       }
       __syncthreads();
+      const EpanBins eb0 = make_epan_bins(zmn, zmx, B, 1.0);
       FuStats u = {0.0, 0.0, 0.0, 0.0, 0.f, 0.f};
-      for (int i = tid; i < B; i += FU_NT) { u.a += bs[i]; u.b += bs[i] * bs[i]; u.c += bc[i]; u.d += bc[i] * bc[i]; }
-      __syncthreads();                                       // `red` was read by every thread after the first reduction
-      u = fu_block_stats(u, red);
+      for (int i = tid; i < B; i += FU_NT) { const double bv = (double)binsf[i], cc = epan_bin_centre(eb0, i); u.a += bv; u.b += bv * bv; u.c += cc; u.d += cc * cc; }
+      u = fu_block_stats(u, red);                            // (`red` was last read before several barriers)
       const double W = u.a, Q = u.b;
       const double cmean = u.c / B;
       const double dstd = sqrt(fmax(u.d / B - cmean * cmean, 0.0));   // std of the BIN CENTRES (math.py:67 on binning1d's output)
@@ -511,19 +562,28 @@ numerator_fused_kernel(const NumArgs a) {
       if (a.bw_method == CHB_BW_SCOTT) bw = pow(neff_k, -0.2) * dstd;
       else if (a.bw_method == CHB_BW_SILVERMAN) bw = pow(neff_k * 3.0 / 4.0, -0.2) * dstd;
       else bw = a.bw_value * dstd;
-      const double s = gauss ? 0.8493218002880191 / bw : 1.0 / bw;
-      const double c = 0.5 * (lb + ub);
-      // pair layout of the binned data set: {x'_a, x'_b, v_a, v_b}, x' = (centre - c) s, v = log2(w/W) | w/W
-      const int Bp = (B + 1) / 2;
-      for (int i = tid; i < Bp; i += FU_NT) {
-        const int ia = 2 * i, ib = 2 * i + 1;
-        const float xa = (float)((bc[ia] - c) * s), xb = (ib < B) ? (float)((bc[ib] - c) * s) : 0.f;
-        const float wa = (float)(bs[ia] / W), wb = (ib < B) ? (float)(bs[ib] / W) : 0.f;
-        bx[i] = gauss ? make_float4(xa, xb, wa > 0.f ? lg2f_(wa) : -INFINITY, wb > 0.f ? lg2f_(wb) : -INFINITY)
-                      : make_float4(xa, xb, wa, wb);
+      if (!gauss) {
+        // Epanechnikov (the reference's default kernel): prefix sums over the bins, O(1) per grid point
+        const EpanBins eb = make_epan_bins(zmn, zmx, B, bw);
+        double* S0 = bc; double* S1 = bc + (B + 2); double* S2 = bc + 2 * (B + 2);
+        if (warp == 0) epan_bins_prefix(eb, binsf, 1.0 / W, S0, S1, S2);
+        __syncthreads();
+        const double scale = norm * 0.75 / bw;
+        for (int g = tid; g < G; g += FU_NT) dens[g] = epan_bins_sum(eb, eg_at(g), S0, S1, S2) * scale;
+      } else {
+        const double s = 0.8493218002880191 / bw;
+        const double c = 0.5 * (lb + ub);
+        // pair layout of the binned data set: {x'_a, x'_b, v_a, v_b}, x' = (centre - c) s, v = log2(w/W)
+        const int Bp = (B + 1) / 2;
+        for (int i = tid; i < Bp; i += FU_NT) {
+          const int ia = 2 * i, ib = 2 * i + 1;
+          const float xa = (float)((epan_bin_centre(eb0, ia) - c) * s), xb = (ib < B) ? (float)((epan_bin_centre(eb0, ib) - c) * s) : 0.f;
+          const float wa = (float)((double)binsf[ia] / W), wb = (ib < B) ? (float)((double)binsf[ib] / W) : 0.f;
+          bx[i] = make_float4(xa, xb, wa > 0.f ? lg2f_(wa) : -INFINITY, wb > 0.f ? lg2f_(wb) : -INFINITY);
+        }
+        __syncthreads();
+        fu_direct(bx, Bp, G, (lb - c) * s, step * s, 1.f, 0.f, true, norm * 0.3989422804014327 / bw, rows, dens);
       }
-      __syncthreads();
-      fu_direct(bx, Bp, G, (lb - c) * s, step * s, 1.f, 0.f, gauss, norm * (gauss ? 0.3989422804014327 : 0.75) / bw, rows, dens);
     }
     __syncthreads();
 
@@ -598,6 +658,203 @@ numerator_fused_kernel(const NumArgs a) {
       }
     }
   }
+}
+
+// ==================================================================================================================
+// 'marginalized' kind with binning (the reference's default options, examples/test1dgalaxies.ipynb): one fused kernel,
+// warp per pixel.  likelihood.py:160-205: per pixel the in-pixel samples are binned on [min z (all samples), max z (pixel)]
+// (utils/math.py:32-46), the ALWAYS-Epanechnikov kde1d of the B bin centres is evaluated on the effective grid of the
+// unmasked statistics, interpolated onto the event grid and integrated against the pixel's catalogue row.
+//   * the samples arrive bucketed by pixel (api.cu prepare()), so a pixel is a contiguous range of the stage;
+//   * the Epanechnikov kernel has compact support and the bin centres are equally spaced: the sum over the bins inside
+//     |g - c_b| <= bw is a difference of prefix sums of {w, w u, w u^2} (fp64, coordinates centred on the pixel and scaled
+//     by 1/bw), O(B + Nz) per pixel instead of O(B G) -- and no grid array: the two effective-grid values an event-grid
+//     point interpolates between are evaluated on the fly;
+//   * no CTA barrier inside the pixel loop (round 1: ~10 barriers per pixel, 15 pixels per unit).
+struct MargPlan { int stage, scratch, per_warp, red, total; };
+__host__ __device__ inline MargPlan make_marg_plan(int Ns, int B) {
+  MargPlan p;
+  const int Bp = (B + 32) & ~31;                 // >= B + 1 entries for the inclusive prefix tables
+  int o = 0;
+  p.stage = o; o += Ns * 8;
+  p.scratch = o; p.per_warp = Bp * 4 + 3 * Bp * 8;        // bins (float) + S0, S1, S2 (double)
+  o += FU_NW * p.per_warp;
+  p.red = o; o += 96 * 8;
+  p.total = o;
+  return p;
+}
+size_t numerator_marg_smem_bytes(const NumArgs& a) { return (size_t)make_marg_plan(a.Ns, a.num_bins).total; }
+bool numerator_marg_supported(const NumArgs& a) {
+  return a.fp_mode == CHB_FP32 && a.kind == CHB_PGW_MARG && a.binning && a.use_cut && (a.Ns % 2 == 0) && a.Nz / 2 >= 2 &&
+         a.num_bins >= 2 && a.s4 != nullptr && a.pix_off != nullptr;
+}
+
+__global__ void __launch_bounds__(FU_NT, 2)
+numerator_marg_kernel(const NumArgs a) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  __shared__ double P[CHB_NPAR];
+  __shared__ double HC[CHB_NHC];
+  __shared__ float FC[CHB_NFC];
+  const TableLayout lay = a.mc.lay;
+  const int Ns = a.Ns, Nz = a.Nz, Pp = a.P, B = a.num_bins, G = Nz / 2;
+  const MargPlan pl = make_marg_plan(Ns, B);
+  float4* stage = reinterpret_cast<float4*>(smraw + pl.stage);
+  const float* stf = reinterpret_cast<const float*>(stage);
+  double* red = reinterpret_cast<double*>(smraw + pl.red);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int Bp = (B + 32) & ~31;
+  float* bins = reinterpret_cast<float*>(smraw + pl.scratch + warp * pl.per_warp);
+  double* S0 = reinterpret_cast<double*>(bins + Bp);
+  double* S1 = S0 + Bp;
+  double* S2 = S1 + Bp;
+  const bool has_cat = (a.mc.catalog_kind == 1);
+  // sample j of the stage: pair j/2, slot j&1 of {dz_a, dz_b, w_a, w_b}
+  auto dz_of = [&](int j) -> float { return stf[4 * (j >> 1) + (j & 1)]; };
+  auto w_of = [&](int j) -> float { return stf[4 * (j >> 1) + 2 + (j & 1)]; };
+
+  const long long units = (long long)a.Nev * a.n_hyper;
+  for (long long unit = blockIdx.x; unit < units; unit += gridDim.x) {
+    const int ev = (int)(unit / a.n_hyper), h = (int)(unit % a.n_hyper);
+    const double* tblk = a.tabs + (size_t)h * lay.total() + lay.off_f32();
+    __syncthreads();
+    if (tid < CHB_NPAR) P[tid] = a.hyper[(size_t)h * CHB_NPAR + tid];
+    else if (tid >= 64 && tid < 64 + CHB_NHC) HC[tid - 64] = a.HC[(size_t)h * CHB_NHC + tid - 64];
+    else if (tid >= 128 && tid < 128 + CHB_NFC) FC[tid - 128] = __ldg(reinterpret_cast<const float*>(tblk + lay.f32_fc()) + tid - 128);
+    __syncthreads();
+    {
+      const size_t so = (size_t)ev * Ns;
+      switch (a.mc.mass_model) {
+        case CHB_MASS_TPL: fu_reweight<CHB_MASS_TPL>(tblk, lay.rc, lay.rcs, lay.rms, lay.rm, FC, a.s4 + so, a.l2 + so, Ns, 0, stage, nullptr, red); break;
+        case CHB_MASS_BPL: fu_reweight<CHB_MASS_BPL>(tblk, lay.rc, lay.rcs, lay.rms, lay.rm, FC, a.s4 + so, a.l2 + so, Ns, 0, stage, nullptr, red); break;
+        default: fu_reweight<CHB_MASS_PLP>(tblk, lay.rc, lay.rcs, lay.rms, lay.rm, FC, a.s4 + so, a.l2 + so, Ns, 0, stage, nullptr, red); break;
+      }
+    }
+    __syncthreads();
+    FuStats st = {0.0, 0.0, 0.0, 0.0, INFINITY, -INFINITY};
+#pragma unroll
+    for (int i = 0; i < FU_NW; ++i) {
+      st.a += red[i * 6 + 0]; st.b += red[i * 6 + 1]; st.c += red[i * 6 + 2]; st.d += red[i * 6 + 3];
+      st.mn = fminf(st.mn, (float)red[i * 6 + 4]); st.mx = fmaxf(st.mx, (float)red[i * 6 + 5]);
+    }
+    const double z0 = red[95];
+    const double s1 = st.a, s2 = st.b;
+    const double zmn = z0 + (double)st.mn, zmx = z0 + (double)st.mx;
+    const double dzmean = st.c / Ns;
+    const double zstd = sqrt(fmax(st.d / Ns - dzmean * dzmean, 0.0));
+    const double norm = s1 / Ns;
+    const double neff = s1 * s1 / s2;
+    double* pout = a.p_gw_out ? a.p_gw_out + ((size_t)h * a.Nev + ev) * (size_t)Pp * Nz : nullptr;
+    if (!(neff >= a.pe_neff)) {
+      if (pout) for (int i = tid; i < Pp * Nz; i += FU_NT) pout[i] = 0.0;
+      if (tid == 0) { a.log_like[(size_t)h * a.Nev + ev] = nan_to_num_log_fu(0.0); a.like_raw[(size_t)h * a.Nev + ev] = 0.0; }
+      continue;
+    }
+    // effective grid of the UNMASKED statistics (likelihood.py:186-190)
+    const double lb = (zmn - a.cut_grid * zstd > 0.0) ? zmn - a.cut_grid * zstd : 1.e-8;
+    const double ub = zmx + a.cut_grid * zstd;
+    const double step = (ub - lb) / (double)(G - 1), inv_step = 1.0 / step;
+    auto eg_at = [&](int i) -> double { return (i == G - 1) ? ub : __dadd_rn(__dmul_rn((double)i, step), lb); };
+    const int npix = a.neff_pix[ev];
+    const int* off = a.pix_off + (size_t)ev * (Pp + 2);
+    const double* gwp = a.gw_pdf + (size_t)ev * Pp;
+    const double* zgr = a.zgrids + (size_t)ev * Nz;
+    const float2* zt = a.zterms ? a.zterms + ((size_t)(h - a.zterms_h0) * a.Nev + ev) * Nz : nullptr;
+    const double fR = HC[HC_FR];
+    const double* pcat_ev = has_cat ? a.p_cat + (size_t)ev * Pp * Nz : nullptr;
+    const double* pcompl_ev = has_cat ? a.P_compl + (size_t)ev * Nz : nullptr;
+    if (pout) {
+      for (int i = tid + npix * Nz; i < Pp * Nz; i += FU_NT) pout[i] = 0.0;       // padded pixel rows
+    }
+    double like_acc = 0.0;
+    for (int p = warp; p < npix; p += FU_NW) {
+      const int o0 = off[p], o1 = off[p + 1];
+      // ---- masked data set of the pixel: max z, then binning1d on [zmn, zmax_in] ------------------------
+      float mxf = -INFINITY;
+      for (int j = o0 + lane; j < o1; j += 32) mxf = fmaxf(mxf, dz_of(j));
+      mxf = warp_max_f32(mxf);
+      const double zmax_in = fmax(z0 + (double)mxf, zmn);                 // masked samples sit at min(z)
+      for (int i = lane; i < Bp; i += 32) bins[i] = 0.f;
+      __syncwarp();
+      const double brange = zmax_in - zmn;
+      for (int j = o0 + lane; j < o1; j += 32) {
+        const double f = floor(((z0 + (double)dz_of(j)) - zmn) / brange * B);
+        if (!isnan(f)) atomicAdd(&bins[(int)fmin(fmax(f, 0.0), (double)(B - 1))], w_of(j));
+      }
+      __syncwarp();
+      // ---- kde1d of the bin centres: w/W, neff, bandwidth from the std of the CENTRES (math.py:62-70) -------
+      const EpanBins eb0 = make_epan_bins(zmn, zmax_in, B, 1.0);
+      double W = 0.0, Q = 0.0, sc = 0.0, sc2 = 0.0;
+      for (int i = lane; i < B; i += 32) { const double b = (double)bins[i], c = epan_bin_centre(eb0, i); W += b; Q += b * b; sc += c; sc2 += c * c; }
+      W = warp_sum(W); Q = warp_sum(Q); sc = warp_sum(sc); sc2 = warp_sum(sc2);
+      const double cmean = sc / B;
+      const double dstd = sqrt(fmax(sc2 / B - cmean * cmean, 0.0));
+      const double neff_k = 1.0 / (Q / (W * W));
+      double bw;
+      if (a.bw_method == CHB_BW_SCOTT) bw = pow(neff_k, -0.2) * dstd;
+      else if (a.bw_method == CHB_BW_SILVERMAN) bw = pow(neff_k * 3.0 / 4.0, -0.2) * dstd;
+      else bw = a.bw_value * dstd;
+      // W == 0 (no weight in the pixel) -> w/W = NaN for every sample in the reference
+      const double scale = (W != 0.0) ? norm * gwp[p] * 0.75 / bw : nan("");
+      const EpanBins eb = make_epan_bins(zmn, zmax_in, B, bw);
+      epan_bins_prefix(eb, bins, 1.0 / W, S0, S1, S2);
+      __syncwarp();
+      auto dens_at = [&](double g) -> double { return epan_bins_sum(eb, g, S0, S1, S2); };
+      for (int k = lane; k < Nz; k += 32) {
+        const double x = zgr[k];
+        double v = 0.0;
+        if (x >= lb && x <= ub) {
+          int i = (int)((x - lb) * inv_step);
+          i = max(0, min(i, G - 2));
+          while (i < G - 2 && x >= eg_at(i + 1)) ++i;
+          while (i > 0 && x < eg_at(i)) --i;
+          const double x0 = eg_at(i), x1 = eg_at(i + 1), dx = x1 - x0;
+          const double f0 = dens_at(x0), f1 = dens_at(x1);
+          v = ((fabs(dx) <= 4.930380657631324e-32) ? f0 : f0 + ((x - x0) / dx) * (f1 - f0)) * scale;
+        }
+        if (pout) pout[(size_t)p * Nz + k] = v;
+        const double pc = has_cat ? pcat_ev[(size_t)p * Nz + k] : 0.0;
+        if (pc == -100.0) continue;
+        float2 zv;
+        if (zt) zv = __ldg(zt + k);
+        else {
+          const double zl = (k > 0) ? zgr[k - 1] : x, zr = (k < Nz - 1) ? zgr[k + 1] : x;
+          const F32Consts fc = make_f32_consts(a.mc, P, HC, tblk);
+          zv = zgrid_terms_f32(fc, make_cosmo_rate_f32(a.mc, P, HC), P, HC, a.mc.cosmo_model, x, 0.5 * (zr - zl));
+        }
+        const double pgal = has_cat ? fR * pc + (1.0 - pcompl_ev[k]) * (double)zv.x : (double)zv.x;
+        like_acc += v * pgal * (double)zv.y;
+      }
+      __syncwarp();
+    }
+    {
+      const double ws = warp_sum(like_acc);
+      __syncthreads();                                       // every warp is done reading `red` (statistics)
+      if (lane == 0) red[warp] = ws;
+      __syncthreads();
+      if (tid == 0) {
+        double like = 0.0;
+#pragma unroll
+        for (int w = 0; w < FU_NW; ++w) like += red[w];
+        a.log_like[(size_t)h * a.Nev + ev] = nan_to_num_log_fu(like); a.like_raw[(size_t)h * a.Nev + ev] = like;
+      }
+    }
+  }
+}
+
+cudaError_t numerator_marg_configure(size_t optin) {
+  cudaFuncAttributes fa;
+  cudaError_t e = cudaFuncGetAttributes(&fa, numerator_marg_kernel);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(numerator_marg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(optin - fa.sharedSizeBytes));
+}
+int numerator_marg_ctas_per_sm(size_t smem) {
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, numerator_marg_kernel, FU_NT, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+cudaError_t launch_numerator_marg(const NumArgs& a, int grid, size_t smem, cudaStream_t s) {
+  numerator_marg_kernel<<<grid, FU_NT, smem, s>>>(a);
+  return cudaGetLastError();
 }
 
 cudaError_t numerator_fused_configure(size_t optin) {      // see numerator_f32_configure

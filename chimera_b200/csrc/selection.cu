@@ -46,15 +46,18 @@ selection_kernel(SelArgs a) {
   const long long j0 = (long long)tile * chunk;
   const long long j1 = min((long long)a.Ninj, j0 + chunk);
   double s1 = 0.0, s2 = 0.0;
+  // table intervals without binary searches (models.cuh upper_index_lut / upper_index_log): bit-identical interpolants
+  const unsigned short* lut = reinterpret_cast<const unsigned short*>(a.tabs + (size_t)h * lay.total() + lay.off_f32() + lay.f32_lut());
+  const int lut_b0 = (int)HC[HC_LUT_B0], lut_nb = (int)HC[HC_LUT_NB];
   for (long long j = j0 + tid; j < j1; j += blockDim.x) {
     const double dL = __ldg(a.dL + j), m1d = __ldg(a.m1d + j), m2d = __ldg(a.m2d + j), pd = __ldg(a.p_draw + j);
-    const double z = interp_clamped(dL, dLt, zg, rc);                  // z_from_dGW
+    const double z = interp_at(dL, dLt, zg, rc, upper_index_lut(dLt, rc, dL, lut, lut_b0, lut_nb));   // z_from_dGW
     const double opz = 1.0 + z;
     const double m1 = m1d / opz, m2 = m2d / opz;                      // theta_det2src
     const double dCt = dL2dCt(cm, P, dL, z);                          // original distances
     const double Ez = E_at_z(P, HC, z);
     const double pz = dVcdz_from(HC, dCt, Ez) * (merger_rate(rmod, P, HC, z) / opz);
-    const double dN = R0 * p_m1m2(mm, P, HC, mg, cdf, rm, m1, m2) * pz;
+    const double dN = R0 * p_m1m2_logidx(mm, P, HC, mg, cdf, rm, m1, m2) * pz;
     const double jac = fabs(ddLdz_from(cm, P, HC, z, dCt, Ez)) * (opz * opz);
     const double w = (dN / jac) / pd;
     if (!isnan(w)) s1 += w;     // nansum for xi (selection_function.py:39)

@@ -264,6 +264,7 @@ def _synthetic(nev, ns, nz, ninj, sky, seed):
   (None, "epan", True, "fp64", 1e-9), (None, "epan", True, "fp32", 1e-3),
   ("approximate", "gauss", False, "fp64", 1e-9), ("approximate", "gauss", False, "fp32", 1e-3),
   ("marginalized", "epan", True, "fp64", 1e-9), ("marginalized", "epan", False, "fp32", 1e-3),
+  ("marginalized", "epan", True, "fp32", 1e-3),
   ("full", "gauss", False, "fp64", 1e-9), ("full", "gauss", False, "fp32", 1e-3),
 ])
 def test_oracle_parity_synthetic(cb, kind, kernel, binning, fp_mode, rtol):

@@ -113,3 +113,31 @@ def test_fused_kernel_pixelated_kinds(cb, kind, kernel, binning):
                             num_bins=200, fp_mode="fp32", options={"fused": 0, "split": 0})
   lle = like.compute_all(H0=H0)[0]
   _check(lle, ref, tol=1e-4)
+
+
+@pytest.mark.parametrize("bw", [None, "silverman", 0.35])
+def test_marginalized_binned_fused_vs_split_and_oracle(cb, bw):
+  """'marginalized' + binning (the reference's default options): the fused warp-per-pixel kernel with the prefix-sum
+  Epanechnikov (default) and the round-1 split kernels (`fused=0`) against the oracle, p_gw arrays included."""
+  from oracle import chimera_oracle as orc
+  from test_gpu_parity import _synthetic
+  ev, zg, inj, N_inj, cat = _synthetic(12, 2000, 160, 20000, True, seed=211)
+  kw = {k: ev[k] for k in ("m1det", "m2det", "dL", "pe_prior", "ra", "dec", "opt_nsides", "pixels_opt_nsides", "ra_pix",
+                           "dec_pix", "gw_loc2d_pdf", "pixels_pe_opt_nside")}
+  gcat = cb.pixelated_catalog(cb.dVdz_completeness(cat["z_range"]), p_cat=cat["p_cat"], P_compl=cat["P_compl"])
+  pop = cb.population(cb.cosmo.flrw(z_max=5.), cb.mass.plp(), cb.rate.madau_dickinson(), gal_cat=gcat)
+  sel = cb.selection_function(cb.theta_inj_det(**inj), N_inj, 5.)
+  pop0 = orc.make_pop(orc.make_cosmo("flrw", z_max=5.), orc.make_mass("plp"), orc.make_rate("madau_dickinson"), catalog=cat)
+  opts = orc.make_opts("marginalized", "epan", bw, 2.0, True, 200, 2.0)
+  H0 = np.array([58., 70., 83.])
+  ref = np.array([orc.compute_all(pop0, ev, zg, opts, inj, N_inj, 5., ev["neff_pixels"], H0=float(h))[0] for h in H0])
+  pgw_ref = orc.p_gw3dmarg(orc.pop_update(pop0, H0=70.), ev, zg, opts)
+  for opt in ({}, {"fused": 0}):
+    like = cb.hyperlikelihood(cb.theta_pe_det(**kw), zg, pop, sel, kind_p_gw3d="marginalized", kernel="epan", bw_method=bw,
+                              binning=True, num_bins=200, fp_mode="fp32", options=opt)
+    _check(like.compute_all(H0=H0)[0], ref, tol=1e-4)
+    pgw = like.p_gw3dmarg(pop.update(H0=70.))
+    scale = np.nanmax(np.abs(pgw_ref))
+    for e in range(pgw_ref.shape[0]):
+      n = int(ev["neff_pixels"][e])
+      np.testing.assert_allclose(pgw[e, :n], pgw_ref[e, :n], rtol=2e-3, atol=2e-5 * scale)
