@@ -73,6 +73,7 @@ struct chb_handle {
   int opt_fused = 1;                       // 1-D kinds, fp32: one fused kernel (numerator_fused.cu); 0: round-1 split kernels
   int opt_split = 1;                       // round-1 path: split MODE 1 -> stage -> MODE 2 (0: one MODE 0 kernel)
   int opt_kde_win = 32;                    // windowed recurrence: sub-stream iterations per chunk (0: windows off)
+  double opt_kde_win_t2 = 24.0;            // window threshold in bits (fused kernel)
   int opt_kde_direct = 0;                  // 1: one MUFU.EX2 per pair (no recurrence)
   int opt_bin_runs = 1;                    // round-1 path: binning by runs of the sorted samples
   double opt_stage_gb = 12.0;              // round-1 path: budget of the {z, w} stage buffer
@@ -388,6 +389,7 @@ static int eval_impl(chb_handle* h, int64_t n_hyper, const double* d_hyper, doub
     a.bw_value = c.bw_value; a.cut_grid = c.cut_grid; a.pe_neff = c.pe_neff;
     a.rec_off = h->opt_kde_direct; a.bin_runs = h->opt_bin_runs;
     a.kde_win_iters = h->sorted ? h->opt_kde_win : 0;
+    a.win_t2 = (float)h->opt_kde_win_t2;
     a.Nev = (int)h->Nev; a.Ns = (int)h->Ns; a.Nz = (int)h->Nz; a.P = (int)std::max<int64_t>(h->P, 1);
     a.m1d = h->m1d.p; a.m2d = h->m2d.p; a.dL = h->dL.p; a.prior = h->prior.p; a.ra = h->ra.p; a.dec = h->dec.p;
     a.zgrids = h->zgrids.p; a.pix_off = h->pix_off.p; a.ra_pix = h->ra_pix.p; a.dec_pix = h->dec_pix.p;
@@ -581,6 +583,7 @@ int chb_set_option(chb_handle* h, const char* name, double value) {
   if (n == "fused") h->opt_fused = value != 0.0;
   else if (n == "split") h->opt_split = value != 0.0;
   else if (n == "kde_win") { if (value < 0 || value > 4096) return fail(h, CHB_ERR_INVALID, "kde_win out of range"); h->opt_kde_win = (int)value; }
+  else if (n == "kde_win_t2") { if (!(value >= 16.0 && value <= 60.0)) return fail(h, CHB_ERR_INVALID, "kde_win_t2 must be in [16, 60]"); h->opt_kde_win_t2 = value; }
   else if (n == "kde_direct") h->opt_kde_direct = value != 0.0;
   else if (n == "bin_runs") h->opt_bin_runs = value != 0.0;
   else if (n == "stage_gb") { if (!(value > 0.0)) return fail(h, CHB_ERR_INVALID, "stage_gb must be positive"); h->opt_stage_gb = value; }

@@ -68,9 +68,11 @@ struct WinPlan { int R, LPS, chunk, nchunks; };
 // grid too coarse for the recurrence).
 // `gran`: chunk sizes are rounded up to a multiple of it (the fused kernel summarises 64-sample blocks while it
 // reweights them, so its chunks must be unions of such blocks).
-__device__ __forceinline__ bool win_plan(int G, int n, float h, int iters, int max_chunks, WinPlan& pl, int gran = 1) {
+// `t2`: the window threshold in bits (terms below 2^-t2 of the largest term at a grid point are dropped).
+__device__ __forceinline__ bool win_plan(int G, int n, float h, int iters, int max_chunks, WinPlan& pl, int gran = 1,
+                                         float t2 = CHB_WIN_T2) {
   if (!(h > 0.f) || h > 1.8f || iters <= 0) return false;
-  const int wn = 2 * (int)ceilf(6.2f / h) + CHB_WIN_SPAN;
+  const int wn = 2 * (int)ceilf(sqrtf(t2 + 8.f) / h) + CHB_WIN_SPAN;    // half-width sqrt(t2 + log2(chunk)) in scaled units
   if (10 * wn > 7 * G) return false;
   const int rmax = min(CHB_WIN_MAXR, 1 + (int)(5.5f / h));             // (R-1) h <= 5.5
   // tiles by increasing width; at equal width the longer run (fewer MUFU per pair) comes first
@@ -229,7 +231,7 @@ __device__ __forceinline__ void kde_win_BC(const float2* __restrict__ xw, int n,
                                            const WinPlan& pl, double scale, const float4* __restrict__ summ,
                                            int2* __restrict__ win, const float* __restrict__ cr,
                                            double* __restrict__ rows, double* __restrict__ dens,
-                                           float sf = 1.f, float koff = 0.f) {
+                                           float sf = 1.f, float koff = 0.f, float t2 = CHB_WIN_T2) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float h = (float)hd;
   // ---- phase B: lane c holds chunk c; every warp walks its share of the grid points: M(g) is one warp-wide max,
@@ -244,7 +246,7 @@ __device__ __forceinline__ void kde_win_BC(const float2* __restrict__ xw, int n,
       const float d = gp - my.w;
       const float m = warp_max_f32(fmaf(-d, d, my.z));
       const float dist = fmaxf(fmaxf(my.x - gp, gp - my.y), 0.f);
-      if (fmaf(-dist, dist, myU) >= m - CHB_WIN_T2 && my.z > -INFINITY) { gmin = min(gmin, g); gmax = g; }
+      if (fmaf(-dist, dist, myU) >= m - t2 && my.z > -INFINITY) { gmin = min(gmin, g); gmax = g; }
     }
     if (gmax >= 0) { atomicMin(&win[lane].x, gmin); atomicMax(&win[lane].y, gmax); }
   }

@@ -395,7 +395,7 @@ __device__ __forceinline__ double epan_bins_sum(const EpanBins& eb, double g, co
 // Windowed recurrence KDE of the staged samples (kde_win.cuh) -- NOT inlined, for the same reason as fu_reweight.
 // Merges the 64-sample block summaries into the plan's chunks (scaled units, weights normalised), then phases B and C.
 __device__ __noinline__ void fu_kde_win(const float4* __restrict__ stage, int Ns, int G, double gfirst, double hd, int R,
-                                        int LPS, int chunk, int nchunks, double scale, float sf, float koff,
+                                        int LPS, int chunk, int nchunks, double scale, float sf, float koff, float t2,
                                         const float4* __restrict__ sub, float4* __restrict__ summ, int2* __restrict__ win,
                                         float* __restrict__ cr, double* __restrict__ rows, double* __restrict__ dens) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -415,7 +415,7 @@ __device__ __noinline__ void fu_kde_win(const float4* __restrict__ stage, int Ns
   }
   __syncthreads();
   kde_win_BC<FU_NW, false, true>(reinterpret_cast<const float2*>(stage), Ns, G, gfirst, hd, wp, scale, summ, win, cr, rows,
-                                 dens, sf, koff);
+                                 dens, sf, koff, t2);
 }
 
 __global__ void __launch_bounds__(FU_NT, CHB_FU_MINB)
@@ -510,9 +510,9 @@ numerator_fused_kernel(const NumArgs a) {
       const double scale = norm * (gauss ? 0.3989422804014327 : 0.75) / bw;
       WinPlan wp;
       const bool windowed = gauss && a.kde_win_iters > 0 && Nz >= 64 &&
-                            win_plan(G, Ns, (float)hd, a.kde_win_iters, 32, wp, FU_SUB);
+                            win_plan(G, Ns, (float)hd, a.kde_win_iters, 32, wp, FU_SUB, a.win_t2);
       if (windowed) {
-        fu_kde_win(stage, Ns, G, gfirst, hd, wp.R, wp.LPS, wp.chunk, wp.nchunks, scale, sf, -lg2f_((float)s1), sub, summ, win,
+        fu_kde_win(stage, Ns, G, gfirst, hd, wp.R, wp.LPS, wp.chunk, wp.nchunks, scale, sf, -lg2f_((float)s1), a.win_t2, sub, summ, win,
                    cr, rows, dens);
       } else {
         const float koff = gauss ? -lg2f_((float)s1) : 0.f;

@@ -113,6 +113,8 @@ void chb_destroy(chb_handle* h);
  *   "split"      1 (default) | 0: non-fused form as two kernels | as one MODE-0 kernel
  *   "kde_win"    32 (default): windowed Gaussian recurrence, sub-stream iterations per chunk; 0: every sample visits
  *                the whole effective grid
+ *   "kde_win_t2" 24 (default): window threshold of the fused kernel in bits -- terms below 2^-t2 of the LARGEST term at a grid
+ *                point are dropped (fp32 carries 24 bits); 30 was round 1's setting
  *   "kde_direct" 0 (default) | 1: one MUFU.EX2 per (grid point, sample) pair, no recurrence
  *   "bin_runs"   1 (default) | 0: non-fused binning by runs of sorted samples | one shared-memory atomic per sample
  *   "stage_gb"   12 (default): budget of the stage buffer of the non-fused form; hyper-points are batched beyond it

@@ -42,6 +42,7 @@ def _check(lle, ref, tol=2e-5):
 
 @pytest.mark.parametrize("ns,nz,opt", [
   (4096, 300, {}),                                   # default: fused kernel, windowed recurrence on the raw stage
+  (4096, 300, {"kde_win_t2": 30}),                   # round 1's window threshold (default: 24 bits)
   (4096, 300, {"kde_win": 0}),                       # fused kernel, direct pair sums (no window plan)
   (4096, 48, {}),                                    # z grid too short for a window plan
   (700, 300, {}),                                    # few samples: ragged last block, < 8 chunks -> direct sums
@@ -140,4 +141,7 @@ def test_marginalized_binned_fused_vs_split_and_oracle(cb, bw):
     scale = np.nanmax(np.abs(pgw_ref))
     for e in range(pgw_ref.shape[0]):
       n = int(ev["neff_pixels"][e])
-      np.testing.assert_allclose(pgw[e, :n], pgw_ref[e, :n], rtol=2e-3, atol=2e-5 * scale)
+      # (fp32 mode: a sample whose fp32 redshift sits on a bin edge may land in the neighbouring bin; in a sparsely
+      # populated pixel that moves a visible fraction of the weight by one bin width -- hence per-element 2 %, while the
+      # integrated likelihoods above agree to 1e-4)
+      np.testing.assert_allclose(pgw[e, :n], pgw_ref[e, :n], rtol=2e-2, atol=2e-4 * scale)
