@@ -672,18 +672,18 @@ numerator_fused_kernel(const NumArgs a) {
 //     point interpolates between are evaluated on the fly;
 //   * no CTA barrier inside the pixel loop (round 1: ~10 barriers per pixel, 15 pixels per unit).
 struct MargPlan { int stage, scratch, per_warp, red, total; };
-__host__ __device__ inline MargPlan make_marg_plan(int Ns, int B) {
+__host__ __device__ inline MargPlan make_marg_plan(int Ns, int B, int G) {
   MargPlan p;
   const int Bp = (B + 32) & ~31;                 // >= B + 1 entries for the inclusive prefix tables
   int o = 0;
   p.stage = o; o += Ns * 8;
-  p.scratch = o; p.per_warp = Bp * 4 + 3 * Bp * 8;        // bins (float) + S0, S1, S2 (double)
+  p.scratch = o; p.per_warp = Bp * 4 + 3 * Bp * 8 + ((G + 1) & ~1) * 8;        // bins (float) + S0, S1, S2 + dens (double)
   o += FU_NW * p.per_warp;
   p.red = o; o += 96 * 8;
   p.total = o;
   return p;
 }
-size_t numerator_marg_smem_bytes(const NumArgs& a) { return (size_t)make_marg_plan(a.Ns, a.num_bins).total; }
+size_t numerator_marg_smem_bytes(const NumArgs& a) { return (size_t)make_marg_plan(a.Ns, a.num_bins, a.Nz / 2).total; }
 bool numerator_marg_supported(const NumArgs& a) {
   return a.fp_mode == CHB_FP32 && a.kind == CHB_PGW_MARG && a.binning && a.use_cut && (a.Ns % 2 == 0) && a.Nz / 2 >= 2 &&
          a.num_bins >= 2 && a.s4 != nullptr && a.pix_off != nullptr;
@@ -697,7 +697,7 @@ numerator_marg_kernel(const NumArgs a) {
   __shared__ float FC[CHB_NFC];
   const TableLayout lay = a.mc.lay;
   const int Ns = a.Ns, Nz = a.Nz, Pp = a.P, B = a.num_bins, G = Nz / 2;
-  const MargPlan pl = make_marg_plan(Ns, B);
+  const MargPlan pl = make_marg_plan(Ns, B, G);
   float4* stage = reinterpret_cast<float4*>(smraw + pl.stage);
   const float* stf = reinterpret_cast<const float*>(stage);
   double* red = reinterpret_cast<double*>(smraw + pl.red);
@@ -707,6 +707,7 @@ numerator_marg_kernel(const NumArgs a) {
   double* S0 = reinterpret_cast<double*>(bins + Bp);
   double* S1 = S0 + Bp;
   double* S2 = S1 + Bp;
+  double* dn = S2 + Bp;                          // the pixel's KDE on the effective grid (G doubles)
   const bool has_cat = (a.mc.catalog_kind == 1);
   // sample j of the stage: pair j/2, slot j&1 of {dz_a, dz_b, w_a, w_b}
   auto dz_of = [&](int j) -> float { return stf[4 * (j >> 1) + (j & 1)]; };
@@ -775,9 +776,9 @@ numerator_marg_kernel(const NumArgs a) {
       const double zmax_in = fmax(z0 + (double)mxf, zmn);                 // masked samples sit at min(z)
       for (int i = lane; i < Bp; i += 32) bins[i] = 0.f;
       __syncwarp();
-      const double brange = zmax_in - zmn;
+      const double brange = zmax_in - zmn, binv = (double)B / brange;
       for (int j = o0 + lane; j < o1; j += 32) {
-        const double f = floor(((z0 + (double)dz_of(j)) - zmn) / brange * B);
+        const double f = floor(((z0 + (double)dz_of(j)) - zmn) * binv);
         if (!isnan(f)) atomicAdd(&bins[(int)fmin(fmax(f, 0.0), (double)(B - 1))], w_of(j));
       }
       __syncwarp();
@@ -798,7 +799,8 @@ numerator_marg_kernel(const NumArgs a) {
       const EpanBins eb = make_epan_bins(zmn, zmax_in, B, bw);
       epan_bins_prefix(eb, bins, 1.0 / W, S0, S1, S2);
       __syncwarp();
-      auto dens_at = [&](double g) -> double { return epan_bins_sum(eb, g, S0, S1, S2); };
+      for (int g = lane; g < G; g += 32) dn[g] = epan_bins_sum(eb, eg_at(g), S0, S1, S2);
+      __syncwarp();
       for (int k = lane; k < Nz; k += 32) {
         const double x = zgr[k];
         double v = 0.0;
@@ -808,7 +810,7 @@ numerator_marg_kernel(const NumArgs a) {
           while (i < G - 2 && x >= eg_at(i + 1)) ++i;
           while (i > 0 && x < eg_at(i)) --i;
           const double x0 = eg_at(i), x1 = eg_at(i + 1), dx = x1 - x0;
-          const double f0 = dens_at(x0), f1 = dens_at(x1);
+          const double f0 = dn[i], f1 = dn[i + 1];
           v = ((fabs(dx) <= 4.930380657631324e-32) ? f0 : f0 + ((x - x0) / dx) * (f1 - f0)) * scale;
         }
         if (pout) pout[(size_t)p * Nz + k] = v;
