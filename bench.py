@@ -80,7 +80,7 @@ def c5_walkers(n=4096, seed=3456):
 def parse():
   ap = argparse.ArgumentParser()
   ap.add_argument("--gpus", type=int, default=1)
-  ap.add_argument("--steps", type=int, default=5)
+  ap.add_argument("--steps", type=int, default=20)
   ap.add_argument("--warmup", type=int, default=3)
   ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
   ap.add_argument("--config", default="C3", choices=list(CONFIGS))
@@ -271,11 +271,14 @@ class ClockSampler:
 
   def __init__(self, index):
     self.rows, self.proc, self.index = [], None, index
+    self.t_begin = self.t_end = None
 
   def start(self):
+    """Launched BEFORE the warm-up steps (nvidia-smi needs ~0.5 s to print its first row); every row is stamped on
+    arrival and stop() keeps the rows that fall inside the timed region [mark_begin, mark_end]."""
     try:
       self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                    "--format=csv,noheader,nounits", "-lms", "100"],
+                                    "--format=csv,noheader,nounits", "-lms", "50"],
                                    stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
       self.thread = threading.Thread(target=self._read, daemon=True)
       self.thread.start()
@@ -284,7 +287,18 @@ class ClockSampler:
 
   def _read(self):
     for line in self.proc.stdout:
-      self.rows.append(line.strip())
+      self.rows.append((time.perf_counter(), line.strip()))
+
+  def wait_first(self, timeout=3.0):
+    t0 = time.perf_counter()
+    while self.proc is not None and not self.rows and time.perf_counter() - t0 < timeout:
+      time.sleep(0.02)
+
+  def mark_begin(self):
+    self.t_begin = time.perf_counter()
+
+  def mark_end(self):
+    self.t_end = time.perf_counter()
 
   def stop(self):
     if self.proc is None:
@@ -294,21 +308,34 @@ class ClockSampler:
       self.proc.wait(timeout=2)
     except Exception:
       self.proc.kill()
-    sm, mx, reasons = [], [], set()
     names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-    for r in self.rows:
-      f = [x.strip() for x in r.split(",")]
-      if len(f) < 7:
-        continue
-      try:
-        sm.append(float(f[0])); mx.append(float(f[1]))
-      except ValueError:
-        continue
-      for nm, val in zip(names, f[3:7]):
-        if val.lower().startswith("active"):
-          reasons.add(nm)
+
+    def parse(rows):
+      sm, mx, reasons = [], [], set()
+      for _, r in rows:
+        f = [x.strip() for x in r.split(",")]
+        if len(f) < 7:
+          continue
+        try:
+          sm.append(float(f[0])); mx.append(float(f[1]))
+        except ValueError:
+          continue
+        for nm, val in zip(names, f[3:7]):
+          if val.lower().startswith("active"):
+            reasons.add(nm)
+      return sm, mx, reasons
+
+    tb = self.t_begin if self.t_begin is not None else -1e300
+    te = self.t_end if self.t_end is not None else 1e300
+    inside = [r for r in self.rows if tb <= r[0] <= te + 0.05]
+    window = "timed region"
+    sm, mx, reasons = parse(inside)
+    if not sm:
+      # a timed region shorter than the sampling period: the rows of the warm-up steps right before it (same load)
+      window = "warm-up + timed region (timed region shorter than one sampling period)"
+      sm, mx, reasons = parse([r for r in self.rows if r[0] <= te + 0.05])
     return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-            "samples": len(sm), "reasons": sorted(reasons)}
+            "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 def measured_peaks():
@@ -347,20 +374,26 @@ def time_steps(like, w, steps, warmup, world, local_rank, sample_clocks=False):
       dist.barrier()
     torch.cuda.synchronize()
 
+  sampler = ClockSampler(local_rank) if sample_clocks else None
+  if sampler:
+    sampler.start()
+    like.partials_device(d_rows, d_part)      # (untimed: keeps the GPU under load while nvidia-smi starts)
+    sampler.wait_first()
   for _ in range(warmup):
     like.partials_device(d_rows, d_part)
   barrier()
   launches0 = like.engine.launches
-  sampler = ClockSampler(local_rank) if sample_clocks else None
-  if sampler:
-    sampler.start()
   e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   barrier()
+  if sampler:
+    sampler.mark_begin()
   e0.record()
   for _ in range(steps):
     like.partials_device(d_rows, d_part)
   e1.record()
   barrier()
+  if sampler:
+    sampler.mark_end()
   ms_total = e0.elapsed_time(e1)
   out = dict(launches=like.engine.launches - launches0, kernel_ms={k: float(v) for k, v in like.engine.timings().items()},
              clocks=sampler.stop() if sampler else None, rows=rows, n_hyper=rows.shape[0])

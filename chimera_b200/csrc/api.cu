@@ -153,6 +153,7 @@ int chb_create(chb_handle** out, const chb_config* cfg) {
     return fail(nullptr, CHB_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
   }
   if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, CHB_ERR_INVALID, "device ordinal out of range");
+  DevGuard _dg;
   if ((e = cudaSetDevice(cfg->device)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaSetDevice");
   chb_handle* h = new chb_handle();
   h->cfg = *cfg;
@@ -169,7 +170,7 @@ int chb_create(chb_handle** out, const chb_config* cfg) {
 
 void chb_destroy(chb_handle* h) {
   if (!h) return;
-  cudaSetDevice(h->cfg.device);
+  DevGuard _dg(h->cfg.device);
   DevBuf<double>* dbl[] = {&h->m1d, &h->m2d, &h->dL, &h->prior, &h->ra, &h->dec, &h->zgrids, &h->ra_pix, &h->dec_pix,
                            &h->gw_pdf, &h->p_cat, &h->P_compl, &h->inj_m1, &h->inj_m2, &h->inj_dL, &h->inj_pd,
                            &h->hyper, &h->tabs, &h->HC, &h->log_like, &h->like_raw, &h->tile_part, &h->partials, &h->pgw, &h->scratch};
@@ -193,7 +194,7 @@ int chb_set_events(chb_handle* h, int64_t Nev, int64_t Ns, int64_t Nz, const dou
   if (!m1det || !m2det || !dL || !pe_prior || !z_grids) return fail(h, CHB_ERR_INVALID, "NULL event array");
   if (h->cfg.kind_p_gw == CHB_PGW_FULL && (!ra || !dec)) return fail(h, CHB_ERR_INVALID, "kind 'full' needs ra/dec samples");
   if (h->cfg.use_cut_grid && Nz / 2 < 2) return fail(h, CHB_ERR_INVALID, "z_int_res//2 must be >= 2");
-  cudaSetDevice(h->cfg.device);
+  DevGuard _dg(h->cfg.device);
   const size_t n = (size_t)Nev * Ns;
   h->Nev = Nev; h->Ns = Ns; h->Nz = Nz;
   h->h_m1.assign(m1det, m1det + n); h->h_m2.assign(m2det, m2det + n);
@@ -213,7 +214,7 @@ int chb_set_pixels(chb_handle* h, int64_t P, const int64_t* pixels_opt_nsides, c
     return fail(h, CHB_ERR_INVALID, "NULL pixel array or P < 1");
   if (h->cfg.kind_p_gw == CHB_PGW_MARG && !pixels_pe_opt_nside)
     return fail(h, CHB_ERR_INVALID, "kind 'marginalized' needs pixels_pe_opt_nside");
-  cudaSetDevice(h->cfg.device);
+  DevGuard _dg(h->cfg.device);
   h->P = P;
   const size_t np = (size_t)h->Nev * P;
   h->h_pixels.assign(pixels_opt_nsides, pixels_opt_nsides + np);
@@ -241,7 +242,7 @@ int chb_set_catalog(chb_handle* h, const double* p_cat, const double* P_compl) {
   if (!h->have_pixels) return fail(h, CHB_ERR_STATE, "chb_set_pixels must come first");
   if (!p_cat || !P_compl) return fail(h, CHB_ERR_INVALID, "NULL catalogue array");
   if (h->cfg.catalog_kind != 1) return fail(h, CHB_ERR_INVALID, "config has catalog_kind=0 (empty catalogue)");
-  cudaSetDevice(h->cfg.device);
+  DevGuard _dg(h->cfg.device);
   CU(h->p_cat.upload(p_cat, (size_t)h->Nev * h->P * h->Nz), "upload p_cat");
   CU(h->P_compl.upload(P_compl, (size_t)h->Nev * h->Nz), "upload P_compl");
   h->have_catalog = true;
@@ -254,7 +255,7 @@ int chb_set_injections(chb_handle* h, int64_t Ninj, const double* m1det, const d
   if (!h) return CHB_ERR_INVALID;
   if (Ninj < 1 || Ninj > 0x7fffffff || !m1det || !m2det || !dL || !p_draw)
     return fail(h, CHB_ERR_INVALID, "bad injection arrays");
-  cudaSetDevice(h->cfg.device);
+  DevGuard _dg(h->cfg.device);
   CU(h->inj_m1.upload(m1det, Ninj), "upload inj m1det");
   CU(h->inj_m2.upload(m2det, Ninj), "upload inj m2det");
   CU(h->inj_dL.upload(dL, Ninj), "upload inj dL");
@@ -597,7 +598,7 @@ int chb_eval_device(chb_handle* h, int64_t n_hyper, const double* d_hyper, doubl
   if (!h) return CHB_ERR_INVALID;
   if (n_hyper < 1 || !d_hyper || !d_partials) return fail(h, CHB_ERR_INVALID, "bad eval arguments");
   if (!h->have_events && !h->have_inj) return fail(h, CHB_ERR_STATE, "nothing to evaluate: set events and/or injections");
-  cudaSetDevice(h->cfg.device);
+  DevGuard _dg(h->cfg.device);
   cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
   return eval_impl(h, n_hyper, d_hyper, d_log_like, d_partials, d_p_gw, s);
 }
@@ -606,7 +607,7 @@ int chb_eval(chb_handle* h, int64_t n_hyper, const double* hyper, double* log_li
   if (!h) return CHB_ERR_INVALID;
   if (n_hyper < 1 || !hyper || !partials) return fail(h, CHB_ERR_INVALID, "bad eval arguments");
   if (!h->have_events && !h->have_inj) return fail(h, CHB_ERR_STATE, "nothing to evaluate: set events and/or injections");
-  cudaSetDevice(h->cfg.device);
+  DevGuard _dg(h->cfg.device);
   cudaStream_t s = h->stream;
   CU(h->hyper.alloc((size_t)n_hyper * CHB_NPAR), "alloc hyper");
   CU(h->partials.alloc((size_t)n_hyper * 3), "alloc partials");
@@ -636,7 +637,7 @@ int chb_eval(chb_handle* h, int64_t n_hyper, const double* hyper, double* log_li
 int chb_last_numlike_evs(chb_handle* h, double* like_evs) {
   if (!h || !like_evs) return CHB_ERR_INVALID;
   if (!h->have_events || h->last_n_hyper < 1 || !h->like_raw.p) return fail(h, CHB_ERR_STATE, "no numerator evaluated yet");
-  cudaSetDevice(h->cfg.device);
+  DevGuard _dg(h->cfg.device);
   CU(cudaStreamSynchronize(h->stream), "synchronize");
   CU(cudaMemcpy(like_evs, h->like_raw.p, (size_t)h->last_n_hyper * h->Nev * sizeof(double), cudaMemcpyDeviceToHost), "D2H like");
   return CHB_OK;
@@ -682,7 +683,7 @@ static int model_tables_device(const chb_config* cfg, const double* params, Mode
   if (rc != CHB_OK) return fail(nullptr, rc, why);
   if (!params) return fail(nullptr, CHB_ERR_INVALID, "params is NULL");
   if (chb_device_count() == 0) return fail(nullptr, CHB_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
-  CU(cudaSetDevice(cfg->device), "cudaSetDevice");
+  CU(cudaSetDevice(cfg->device), "cudaSetDevice");      // (the callers hold a DevGuard)
   mc = model_cfg(*cfg);
   CU(dP.upload(params, CHB_NPAR), "upload params");
   CU(dT.alloc(mc.lay.total()), "alloc tables");
@@ -698,6 +699,7 @@ int chb_model_eval(const chb_config* cfg, int which, const double* params, int64
   if ((which == CHB_F_P_M1M2 && !b) || (which == CHB_F_POP_RATE_DET_INJ && (!b || !c)))
     return fail(nullptr, CHB_ERR_INVALID, "missing array argument");
   ModelCfg mc;
+  DevGuard _dg;
   DevBuf<double> dP, dT, dHC, da, db, dc, dout;
   int rc = model_tables_device(cfg, params, mc, dP, dT, dHC);
   if (rc == CHB_OK && n > 0) {
@@ -721,6 +723,7 @@ int chb_model_eval(const chb_config* cfg, int which, const double* params, int64
 int chb_model_tables(const chb_config* cfg, const double* params, double* z_grid_interp, double* integral_invE_interp,
                      double* m_grid, double* cdf_m2_conditioned, double* norm_p_m1) {
   ModelCfg mc;
+  DevGuard _dg;
   DevBuf<double> dP, dT, dHC;
   int rc = model_tables_device(cfg, params, mc, dP, dT, dHC);
   if (rc == CHB_OK) {
@@ -742,7 +745,7 @@ int chb_model_tables(const chb_config* cfg, const double* params, double* z_grid
 
 int chb_phase_profile(chb_handle* h, int enable, double out[8]) {
   if (!h) return CHB_ERR_INVALID;
-  cudaSetDevice(h->cfg.device);
+  DevGuard _dg(h->cfg.device);
   if (out) {
     for (int i = 0; i < 8; ++i) out[i] = 0.0;
     if (h->want_prof && h->prof.p && h->num_grid > 0) {
@@ -761,7 +764,7 @@ int64_t chb_kernel_launch_count(const chb_handle* h) { return h ? h->launches : 
 
 int chb_last_timings(const chb_handle* h, double out[8]) {
   if (!h || !out) return CHB_ERR_INVALID;
-  cudaSetDevice(h->cfg.device);
+  DevGuard _dg(h->cfg.device);
   if (cudaEventSynchronize(h->ev[4]) != cudaSuccess) { cudaGetLastError(); return CHB_ERR_STATE; }
   for (int i = 0; i < 8; ++i) out[i] = 0.0;
   for (int i = 0; i < 4; ++i) {

@@ -1,6 +1,7 @@
 // common.cuh -- argument blocks and launcher prototypes shared by the kernels and the C ABI.
 #pragma once
 #include "models.cuh"
+#include "devguard.cuh"
 
 struct ModelCfg {
   int cosmo_model, mass_model, rate_model;

@@ -1,6 +1,7 @@
 // microbench.cu -- measured denominators for the roofline report.
 // chb_mufu_peak: sustained MUFU.EX2 throughput of the device (the bound of the Gaussian KDE pair
 // sum: one ex2 per pair).  8 independent chains per thread, 2048 threads per SM resident.
+#include "common.cuh"
 #include <cuda_runtime.h>
 #include "../../include/chimera_b200.h"
 
@@ -22,7 +23,7 @@ extern "C" int chb_mufu_peak(int device, double seconds, double* exp_per_s) {
   if (!exp_per_s) return CHB_ERR_INVALID;
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) { cudaGetLastError(); return CHB_ERR_CUDA; }
-  cudaSetDevice(device);
+  DevGuard _dg(device);
   int sms = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
   float* d = nullptr;

@@ -32,6 +32,9 @@
 #ifndef CHB_FU_MINB
 #define CHB_FU_MINB 3             // co-resident CTAs per SM the kernel is compiled for
 #endif
+#ifndef CHB_FU_L1PF
+#define CHB_FU_L1PF 1             // 1: at the start of a unit every thread issues prefetch.global.L1 for the table rows the
+#endif                            //    unit is about to touch (a hint: the rows' first uses then hit L1 instead of waiting on L2)
 #ifndef CHB_FU_PREFETCH
 #define CHB_FU_PREFETCH 0         // 1: the next block's packed samples are requested one block ahead (two register sets);
 #endif                            // 0 (default, measured 1 % faster): every block requests its successor's samples right after
@@ -122,9 +125,13 @@ __device__ __forceinline__ FuTab make_fu_tab(const TableLayout& lay, const doubl
 
 // z_from_dGW (cosmo.py:260-264): float-bits LUT -> candidate row, one scan step (64 buckets per octave of dL hold at
 // most one knot of the 140-per-decade table), rare longer scans in a loop; clamped ends like numpy.interp.
+__device__ __forceinline__ void fu_prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ int fu_lut_bucket(const FuTab& t, float dL) {
+  const int b = (int)(__float_as_uint(dL) >> CHB_LUT_SHIFT) - t.b0;
+  return max(0, min(b, t.nb - 1));
+}
 __device__ __forceinline__ float fu_z_from_dL(const FuTab& t, float dL) {
-  int b = (int)(__float_as_uint(dL) >> CHB_LUT_SHIFT) - t.b0;
-  b = max(0, min(b, t.nb - 1));
+  const int b = fu_lut_bucket(t, dL);
   int k = __ldg(t.lut + b);
   float4 e = __ldg(t.dl4 + k);
   if (dL >= e.w && k < t.rc - 2) { ++k; e = __ldg(t.dl4 + k); }
@@ -187,7 +194,27 @@ __device__ __noinline__ void fu_reweight(const double* __restrict__ f32blk, int 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // z shifted by the redshift of the event's median-dL sample: {z - z0} is exact in fp32 and small, so the one-pass
   // variance does not cancel and the scaled coordinates of the pair sums keep ~1e-6 absolute accuracy
-  const float z0 = fu_z_from_dL(t, __ldg(&s4[Ns / 2].x));
+  const float4 smed = __ldg(&s4[Ns / 2]);
+  const float z0 = fu_z_from_dL(t, smed.x);
+#if CHB_FU_L1PF
+  {
+    // L1 prefetch of the table rows this unit is about to touch (hints only; 128-byte lines = 8 float4 rows / 64 LUT
+    // entries): the LUT entries and dl4 rows between the smallest and the largest dL of the event (its first and last
+    // sample when sorted; min/max otherwise cost nothing but coverage), and the cd4 rows within +-30 % of the median
+    // sample's source-frame primary mass.  Without it the first use of every row waits on L2 inside the dependency
+    // chain of a block (2-3 new dl4 rows per 64 sorted samples).
+    const float dlo = fminf(__ldg(&s4[0].x), __ldg(&s4[Ns - 1].x)), dhi = fmaxf(__ldg(&s4[0].x), __ldg(&s4[Ns - 1].x));
+    const int blo = fu_lut_bucket(t, dlo), bhi = fu_lut_bucket(t, dhi);
+    const int tid = threadIdx.x;
+    if (tid * 64 <= bhi - blo + 64) fu_prefetch_l1(t.lut + min(blo + tid * 64, t.nb - 1));
+    const int klo = __ldg(t.lut + blo), khi = min((int)__ldg(t.lut + bhi) + 3, t.rc - 1);
+    if (tid * 8 <= khi - klo + 8) fu_prefetch_l1(t.dl4 + min(klo + tid * 8, t.rc - 1));
+    const float m1s = smed.y * rcpf_(1.f + z0);
+    const int imed = (int)((lg2f_(m1s) - t.lg2_m0) * t.inv_lg2_mstep);
+    const int ilo = max(0, min(imed - 128, t.rm - 1)), ihi = max(0, min(imed + 128, t.rm - 1));
+    if (tid * 8 <= ihi - ilo + 8) fu_prefetch_l1(t.cd4 + min(ilo + tid * 8, t.rm - 1));
+  }
+#endif
   float fa = 0.f, fb = 0.f, fcs = 0.f, fd = 0.f, mn = INFINITY, mx = -INFINITY;
   // One 64-sample block: `sa, sb, ll` hold the block's packed samples (requested one block earlier), the NEXT block
   // of this warp is requested into `na, nb, nl` before this one is evaluated (L2 latency behind ~300 instructions).

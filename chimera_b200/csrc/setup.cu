@@ -18,6 +18,7 @@
 #include <thrust/sequence.h>
 #include <thrust/sort.h>
 #include "../../include/chimera_b200.h"
+#include "devguard.cuh"
 
 int chb_fail_global(int code, const char* msg);      // api.cu
 
@@ -351,6 +352,7 @@ int chb_healpix_ang2pix_ring(int device, int64_t nside, int64_t n, const double*
   if (n < 0 || (n > 0 && (!theta || !phi || !pix))) return chb_fail_global(CHB_ERR_INVALID, "bad array arguments");
   for (int64_t i = 0; i < n; ++i)
     if (!(theta[i] >= 0.0 && theta[i] <= SPI)) return chb_fail_global(CHB_ERR_INVALID, "theta out of range [0, pi]");
+  DevGuard _dg;
   int rc = pick_device(device);
   if (rc != CHB_OK || n == 0) return rc;
   Buf dt, dp, dx;
@@ -369,6 +371,7 @@ int chb_healpix_pix2ang_ring(int device, int64_t nside, int64_t n, const int64_t
   const int64_t npix = 12 * nside * nside;
   for (int64_t i = 0; i < n; ++i)
     if (pix[i] < 0 || pix[i] >= npix) return chb_fail_global(CHB_ERR_INVALID, "pixel index out of range");
+  DevGuard _dg;
   int rc = pick_device(device);
   if (rc != CHB_OK || n == 0) return rc;
   Buf dt, dp, dx;
@@ -390,6 +393,7 @@ int chb_pixelize_samples(int device, int64_t Nev, int64_t Ns, int64_t P, const i
   if (!pixels_pe_opt_nside && !gw_loc2d_pdf) return chb_fail_global(CHB_ERR_INVALID, "no output requested");
   for (int64_t e = 0; e < Nev; ++e)
     if (!pow2(opt_nsides[e])) return chb_fail_global(CHB_ERR_INVALID, "nside must be a positive power of 2");
+  DevGuard _dg;
   int rc = pick_device(device);
   if (rc != CHB_OK) return rc;
   const size_t ns = (size_t)Nev * Ns, np = (size_t)Nev * P;
@@ -436,6 +440,7 @@ int chb_precompute_p_cat(int device, int64_t Nev, int64_t P, int64_t Nz, const d
     if (neff_pixels[e] < 0 || neff_pixels[e] > P) return chb_fail_global(CHB_ERR_INVALID, "neff_pixels out of range");
     by_nside[opt_nsides[e]].push_back((int)e);
   }
+  DevGuard _dg;
   int rc = pick_device(device);
   if (rc != CHB_OK) return rc;
   const size_t npz = (size_t)Nev * P * Nz;
