@@ -33,7 +33,7 @@
 #define CHB_FU_MINB 3             // co-resident CTAs per SM the kernel is compiled for
 #endif
 #ifndef CHB_FU_L1PF
-#define CHB_FU_L1PF 1             // 1: at the start of a unit every thread issues prefetch.global.L1 for the table rows the
+#define CHB_FU_L1PF 0             // 1: at the start of a unit every thread issues prefetch.global.L1 for the table rows the
 #endif                            //    unit is about to touch (a hint: the rows' first uses then hit L1 instead of waiting on L2)
 #ifndef CHB_FU_PREFETCH
 #define CHB_FU_PREFETCH 0         // 1: the next block's packed samples are requested one block ahead (two register sets);
