@@ -707,6 +707,9 @@ def run_ours(args, rank, world, local_rank):
                             "metric": "|d log L| / max(|log L|, 1) per (event, hyper-point)", "units": int(fin.sum())}
   elif world == 1:
     line["parity_check"] = parity_check(w, like, 16, 4, procs=min(os.cpu_count() or 1, 8))
+  lle32_all = None
+  if world == 1 and "C3_fp64" in subs and args.fp_mode == "fp32":
+    lle32_all = like.compute_all(**w["hyper"])[0]
   del like
   torch.cuda.empty_cache()
   configs = {}
@@ -716,6 +719,15 @@ def run_ours(args, rank, world, local_rank):
         continue
       if s == "C3_fp64":
         configs[s], _ = sub_record("C3", args, "fp64", local_rank, float(peak[0]), base=w, parity=(8, 2))
+        if lle32_all is not None:
+          # every unit of the headline configuration: the timed fp32 mode against the fp64 mode (itself held to the oracle)
+          l64 = build_likelihood(w, "fp64").compute_all(**w["hyper"])[0]
+          fin = np.isfinite(l64) & (np.abs(l64) < 1e300)
+          configs[s]["fp32_vs_fp64_all_units"] = {
+            "units": int(l64.size), "finite_units": int(fin.sum()),
+            "non_finite_classes_match": bool(np.array_equal(fin, np.isfinite(lle32_all) & (np.abs(lle32_all) < 1e300))),
+            "max_err": float(np.max(np.abs(lle32_all[fin] - l64[fin]) / np.maximum(np.abs(l64[fin]), 1.0))),
+            "metric": "|d log L| / max(|log L|, 1) per (event, hyper-point), fp32 mode vs fp64 mode"}
       elif s == "C3_refdefault":
         configs[s], _ = sub_record("C3", args, args.fp_mode, local_rank, float(peak[0]), kernel="epan", binning=True, base=w,
                                    parity=(8, 2), options=opts)

@@ -561,6 +561,18 @@ static int eval_impl(chb_handle* h, int64_t n_hyper, const double* d_hyper, doub
     long long want = (4LL * h->sm_count + n_hyper - 1) / n_hyper;
     long long maxt = std::max<long long>(1, h->Ninj / 1024);
     tiles = (int)std::max<long long>(1, std::min(want, maxt));
+    // ... and a CTA count that fills whole waves: among want .. 6 want tiles the one whose last wave is fullest
+    // (C3: 256 hyper-points x 3 tiles on 444 resident CTAs was 1.73 waves, i.e. a 14 % tail)
+    const int per_sm = selection_ctas_per_sm(h->mc, c.fp_mode);
+    if (per_sm > 0) {
+      const long long slots = (long long)per_sm * h->sm_count;
+      double best = 0.0;
+      for (long long t = tiles; t <= std::min(maxt, 6 * std::max<long long>(want, 1)); ++t) {
+        const long long ctas = t * n_hyper, waves = (ctas + slots - 1) / slots;
+        const double eff = (double)ctas / (double)(waves * slots);
+        if (eff > best + 0.02) { best = eff; tiles = (int)t; }
+      }
+    }
     CU(h->tile_part.alloc((size_t)n_hyper * tiles * 2), "alloc selection partials");
     SelArgs sa;
     sa.mc = h->mc; sa.Ninj = (int)h->Ninj; sa.n_hyper = (int)n_hyper; sa.tiles = tiles;

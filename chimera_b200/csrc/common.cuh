@@ -75,6 +75,7 @@ struct SelArgs {
 cudaError_t launch_build_tables(const ModelCfg& mc, int n_hyper, const double* d_hyper, double* d_tabs,
                                 double* d_HC, cudaStream_t s);
 cudaError_t launch_selection(const SelArgs& a, cudaStream_t s);
+int selection_ctas_per_sm(const ModelCfg& mc, int fp_mode);      // co-resident CTAs of the selection kernel (0: query failed)
 cudaError_t launch_numerator(const NumArgs& a, int grid, int block, size_t smem, cudaStream_t s);
 size_t numerator_smem_bytes(const NumArgs& a, bool stage_in_smem);
 long long numerator_scratch_doubles(const NumArgs& a);

@@ -699,7 +699,7 @@ numerator_f32_kernel(const NumArgs a) {
       const double* rap = a.ra_pix + (size_t)ev * Pp;
       const double* dep = a.dec_pix + (size_t)ev * Pp;
       const int npts = npix * nmask;
-      constexpr int FR = 2;
+      constexpr int FR = 4;                       // evaluation points per lane: two packed pairs (FADD2 / FMUL2 / FFMA2)
       const double enorm = exp(lognorm) * norm;
       const int ntiles = (npts + 32 * FR - 1) / (32 * FR);
       for (int t = warp; t < ntiles; t += NW) {
@@ -719,16 +719,29 @@ numerator_f32_kernel(const NumArgs a) {
             q2[r] = (float)((r2 * l22) * ps);
           }
         }
+        // Two points per packed operand: the same d0^2 + d1^2 + d2^2 (same operation order and roundings as the scalar
+        // form) in 6 packed instructions per two pairs instead of 12, so the loop is bound by MUFU.EX2, not by issue.
+        f32x2 nq0[FR / 2], nq1[FR / 2], nq2[FR / 2], acc2[FR / 2];
+#pragma unroll
+        for (int r = 0; r < FR / 2; ++r) {
+          nq0[r] = pk2(-q0[2 * r], -q0[2 * r + 1]); nq1[r] = pk2(-q1[2 * r], -q1[2 * r + 1]);
+          nq2[r] = pk2(-q2[2 * r], -q2[2 * r + 1]); acc2[r] = 0ull;
+        }
 #pragma unroll 4
         for (int j = 0; j < Ns; ++j) {
           const float4 v = yw[j];
+          const f32x2 vx = pk2(v.x, v.x), vy = pk2(v.y, v.y), vz = pk2(v.z, v.z), vw = pk2(v.w, v.w);
 #pragma unroll
-          for (int r = 0; r < FR; ++r) {
-            const float d0 = v.x - q0[r], d1 = v.y - q1[r], d2 = v.z - q2[r];
-            const float e = fmaf(d2, d2, fmaf(d1, d1, d0 * d0));
-            acc[r] = fmaf(v.w, ex2_ftz(-e), acc[r]);
+          for (int r = 0; r < FR / 2; ++r) {
+            const f32x2 d0 = add2(vx, nq0[r]), d1 = add2(vy, nq1[r]), d2 = add2(vz, nq2[r]);
+            const f32x2 e = fma2(d2, d2, fma2(d1, d1, mul2(d0, d0)));
+            float e0, e1;
+            upk2(e, e0, e1);
+            acc2[r] = fma2(vw, pk2(ex2_ftz(-e0), ex2_ftz(-e1)), acc2[r]);
           }
         }
+#pragma unroll
+        for (int r = 0; r < FR / 2; ++r) upk2(acc2[r], acc[2 * r], acc[2 * r + 1]);
 #pragma unroll
         for (int r = 0; r < FR; ++r) {
           if (pk[r] < 0) continue;

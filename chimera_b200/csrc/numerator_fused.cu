@@ -29,12 +29,17 @@
 #endif
 #define FU_NW (FU_NT / 32)
 #define FU_SUB 64                 // samples per warp iteration of the reweighting loop = granularity of the chunk summaries
+#define FU_INB (FU_SUB * 24)      // bytes of one block of packed samples: 64 x (float4 s4 + float2 l2)
 #ifndef CHB_FU_MINB
 #define CHB_FU_MINB 3             // co-resident CTAs per SM the kernel is compiled for
 #endif
 #ifndef CHB_FU_L1PF
 #define CHB_FU_L1PF 0             // 1: at the start of a unit every thread issues prefetch.global.L1 for the table rows the
 #endif                            //    unit is about to touch (a hint: the rows' first uses then hit L1 instead of waiting on L2)
+#ifndef CHB_FU_CPASYNC
+#define CHB_FU_CPASYNC 1          // 1: every warp stages its NEXT 64-sample block of packed samples in shared memory with
+#endif                            //    cp.async (1.5 KB per warp, issued a whole block ahead: the L2 latency of the sample stream is
+                                  //    off the critical path and no second register set is needed); 0: direct ld.global.cg
 #ifndef CHB_FU_PREFETCH
 #define CHB_FU_PREFETCH 0         // 1: the next block's packed samples are requested one block ahead (two register sets);
 #endif                            // 0 (default, measured 1 % faster): every block requests its successor's samples right after
@@ -49,7 +54,8 @@ __host__ __device__ inline FusedPlan make_fused_plan(int Ns, int Nz, int B) {
   const int Bp = (B + 1) & ~1;
   int o = 0;
   p.stage = o; o += Ns * 8;                       // float4 per two samples {dz_a, dz_b, v_a, v_b}
-  p.rows = o; o += FU_NW * G * 8;                 // per-warp partial rows (doubles)
+  p.rows = o; o += max(FU_NW * G * 8, FU_NW * FU_INB);   // per-warp partial rows (doubles); during the reweighting: the
+                                                         // cp.async landing zone of the packed samples (FU_INB bytes per warp)
   p.dens = o; o += ((G + 1) & ~1) * 8;
   p.bc = o; o += 3 * (B + 2) * 8;                 // inclusive prefix sums S0 | S1 | S2 over the bins (Epanechnikov)
   p.bs = o; o += Bp * 8;
@@ -178,6 +184,12 @@ __device__ __forceinline__ float fu_weight(const FuTab& t, float m1, float m2, f
   return in ? p1 * p2 * inv_prior : 0.f;
 }
 
+__device__ __forceinline__ void fu_cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void fu_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void fu_cp_async_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // One pass over the event's packed samples: {z - z0, v} pairs to the shared-memory stage (v = log2 w when `want_lw`,
 // else w), per-warp statistics {sum w, sum w^2, sum dz, sum dz^2, min dz, max dz} to red[warp*6..] (+ z0 in red[95]), and
 // per 64-sample block {min dz, max dz, max log2 w, dz of that sample} over the samples with w > 0.  Static round-robin
@@ -187,7 +199,7 @@ template <int MASS>
 __device__ __noinline__ void fu_reweight(const double* __restrict__ f32blk, int rc, int rcs, int rms, int rm,
                                          const float* __restrict__ FC, const float4* __restrict__ s4,
                                          const float2* __restrict__ l2, int Ns, int want_lw_i, float4* __restrict__ stage,
-                                         float4* __restrict__ sub, double* __restrict__ red) {
+                                         float4* __restrict__ sub, double* __restrict__ red, float4* __restrict__ inb) {
   TableLayout lay; lay.rc = rc; lay.rm = rm; lay.rcs = rcs; lay.rms = rms;
   const FuTab t = make_fu_tab(lay, f32blk, FC);
   const bool want_lw = want_lw_i != 0;
@@ -265,6 +277,27 @@ __device__ __noinline__ void fu_reweight(const double* __restrict__ f32blk, int 
   };
   int cb = warp * FU_SUB;
   float4 a0, a1, a2, b0, b1, b2;
+#if CHB_FU_CPASYNC
+  // `inb`: this warp's landing zone, 96 float4 = [lane] s4 of the lane's first sample | [32 + lane] second sample |
+  // [64 + lane] the two {log2 m1det, log2 m2det} pairs.  Every lane copies and reads ONLY its own three 16-byte pieces, so
+  // cp.async.wait_group orders everything (no warp barrier); the block after next is requested as soon as the current
+  // one sits in registers, a whole block of arithmetic before it is needed.
+  auto request = [&](int c) {
+    const int j = min(c + 2 * lane, Ns - 2);                   // tail lanes recompute the last pair, never stored
+    fu_cp_async16(inb + lane, s4 + j); fu_cp_async16(inb + 32 + lane, s4 + j + 1);
+    fu_cp_async16(inb + 64 + lane, reinterpret_cast<const float4*>(l2 + j));
+    fu_cp_async_commit();
+  };
+  if (cb < Ns) request(cb);
+  while (cb < Ns) {
+    fu_cp_async_wait();
+    a0 = inb[lane]; a1 = inb[32 + lane]; a2 = inb[64 + lane];
+    const int nb_ = cb + FU_NW * FU_SUB;
+    if (nb_ < Ns) request(nb_);
+    block(cb, a0, a1, a2, b0, b1, b2);
+    cb = nb_;
+  }
+#else
   if (cb < Ns) {
     const int j = min(cb + 2 * lane, Ns - 2);
     a0 = __ldcg(s4 + j); a1 = __ldcg(s4 + j + 1); a2 = __ldcg(reinterpret_cast<const float4*>(l2 + j));
@@ -286,6 +319,7 @@ __device__ __noinline__ void fu_reweight(const double* __restrict__ f32blk, int 
       a0 = __ldcg(s4 + j); a1 = __ldcg(s4 + j + 1); a2 = __ldcg(reinterpret_cast<const float4*>(l2 + j));
     }
   }
+#endif
 #endif
   // warp-level reduction; fp64 from here on
   double da = (double)fa, db = (double)fb, dc = (double)fcs, dd = (double)fd;
@@ -468,6 +502,7 @@ numerator_fused_kernel(const NumArgs a) {
   double* red = reinterpret_cast<double*>(smraw + pl.red);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float4* inb = reinterpret_cast<float4*>(smraw + pl.rows + warp * FU_INB);      // (the rows are zeroed after the reweighting)
   const bool pixelated = (a.kind != CHB_PGW_1D);
   const bool has_cat = (a.mc.catalog_kind == 1);
   const bool gauss = (a.kernel == CHB_KERNEL_GAUSS);
@@ -481,19 +516,19 @@ numerator_fused_kernel(const NumArgs a) {
     if (tid < CHB_NPAR) P[tid] = a.hyper[(size_t)h * CHB_NPAR + tid];
     else if (tid >= 64 && tid < 64 + CHB_NHC) HC[tid - 64] = a.HC[(size_t)h * CHB_NHC + tid - 64];
     else if (tid >= 128 && tid < 128 + CHB_NFC) FC[tid - 128] = __ldg(reinterpret_cast<const float*>(tblk + lay.f32_fc()) + tid - 128);
-    for (int i = tid; i < FU_NW * G; i += FU_NT) rows[i] = 0.0;
     __syncthreads();
 
     // ---- stage 1: reweighting ---------------------------------------------------------------
     {
       const size_t so = (size_t)ev * Ns;
       switch (a.mc.mass_model) {
-        case CHB_MASS_TPL: fu_reweight<CHB_MASS_TPL>(tblk, lay.rc, lay.rcs, lay.rms, lay.rm, FC, a.s4 + so, a.l2 + so, Ns, want_lw, stage, sub, red); break;
-        case CHB_MASS_BPL: fu_reweight<CHB_MASS_BPL>(tblk, lay.rc, lay.rcs, lay.rms, lay.rm, FC, a.s4 + so, a.l2 + so, Ns, want_lw, stage, sub, red); break;
-        default: fu_reweight<CHB_MASS_PLP>(tblk, lay.rc, lay.rcs, lay.rms, lay.rm, FC, a.s4 + so, a.l2 + so, Ns, want_lw, stage, sub, red); break;
+        case CHB_MASS_TPL: fu_reweight<CHB_MASS_TPL>(tblk, lay.rc, lay.rcs, lay.rms, lay.rm, FC, a.s4 + so, a.l2 + so, Ns, want_lw, stage, sub, red, inb); break;
+        case CHB_MASS_BPL: fu_reweight<CHB_MASS_BPL>(tblk, lay.rc, lay.rcs, lay.rms, lay.rm, FC, a.s4 + so, a.l2 + so, Ns, want_lw, stage, sub, red, inb); break;
+        default: fu_reweight<CHB_MASS_PLP>(tblk, lay.rc, lay.rcs, lay.rms, lay.rm, FC, a.s4 + so, a.l2 + so, Ns, want_lw, stage, sub, red, inb); break;
       }
     }
     __syncthreads();                                         // publishes stage[], sub[] and the warp partials
+    for (int i = tid; i < FU_NW * G; i += FU_NT) rows[i] = 0.0;     // (every KDE routine has a barrier before it adds to them)
     FuStats st = {0.0, 0.0, 0.0, 0.0, INFINITY, -INFINITY};
 #pragma unroll
     for (int i = 0; i < FU_NW; ++i) {
@@ -704,7 +739,7 @@ __host__ __device__ inline MargPlan make_marg_plan(int Ns, int B, int G) {
   const int Bp = (B + 32) & ~31;                 // >= B + 1 entries for the inclusive prefix tables
   int o = 0;
   p.stage = o; o += Ns * 8;
-  p.scratch = o; p.per_warp = Bp * 4 + 3 * Bp * 8 + ((G + 1) & ~1) * 8;        // bins (float) + S0, S1, S2 + dens (double)
+  p.scratch = o; p.per_warp = max(Bp * 4 + 3 * Bp * 8 + ((G + 1) & ~1) * 8, FU_INB);   // bins (float) + S0, S1, S2 + dens (double); >= the cp.async landing zone
   o += FU_NW * p.per_warp;
   p.red = o; o += 96 * 8;
   p.total = o;
@@ -735,6 +770,7 @@ numerator_marg_kernel(const NumArgs a) {
   double* S1 = S0 + Bp;
   double* S2 = S1 + Bp;
   double* dn = S2 + Bp;                          // the pixel's KDE on the effective grid (G doubles)
+  float4* inb = reinterpret_cast<float4*>(bins);  // cp.async landing zone of the reweighting (the scratch is idle then)
   const bool has_cat = (a.mc.catalog_kind == 1);
   // sample j of the stage: pair j/2, slot j&1 of {dz_a, dz_b, w_a, w_b}
   auto dz_of = [&](int j) -> float { return stf[4 * (j >> 1) + (j & 1)]; };
@@ -752,9 +788,9 @@ numerator_marg_kernel(const NumArgs a) {
     {
       const size_t so = (size_t)ev * Ns;
       switch (a.mc.mass_model) {
-        case CHB_MASS_TPL: fu_reweight<CHB_MASS_TPL>(tblk, lay.rc, lay.rcs, lay.rms, lay.rm, FC, a.s4 + so, a.l2 + so, Ns, 0, stage, nullptr, red); break;
-        case CHB_MASS_BPL: fu_reweight<CHB_MASS_BPL>(tblk, lay.rc, lay.rcs, lay.rms, lay.rm, FC, a.s4 + so, a.l2 + so, Ns, 0, stage, nullptr, red); break;
-        default: fu_reweight<CHB_MASS_PLP>(tblk, lay.rc, lay.rcs, lay.rms, lay.rm, FC, a.s4 + so, a.l2 + so, Ns, 0, stage, nullptr, red); break;
+        case CHB_MASS_TPL: fu_reweight<CHB_MASS_TPL>(tblk, lay.rc, lay.rcs, lay.rms, lay.rm, FC, a.s4 + so, a.l2 + so, Ns, 0, stage, nullptr, red, inb); break;
+        case CHB_MASS_BPL: fu_reweight<CHB_MASS_BPL>(tblk, lay.rc, lay.rcs, lay.rms, lay.rm, FC, a.s4 + so, a.l2 + so, Ns, 0, stage, nullptr, red, inb); break;
+        default: fu_reweight<CHB_MASS_PLP>(tblk, lay.rc, lay.rcs, lay.rms, lay.rm, FC, a.s4 + so, a.l2 + so, Ns, 0, stage, nullptr, red, inb); break;
       }
     }
     __syncthreads();

@@ -142,6 +142,22 @@ selection_f32_kernel(SelArgs a) {
   }
 }
 
+int selection_ctas_per_sm(const ModelCfg& mc, int fp_mode) {
+  int n = 0;
+  cudaError_t e;
+  if (fp_mode == CHB_FP32) {
+    const size_t smem = (size_t)(mc.lay.f32_total() - mc.lay.f32_dl4()) * sizeof(double);
+    e = cudaFuncSetAttribute(selection_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, selection_f32_kernel, 256, smem);
+  } else {
+    const size_t smem = (size_t)mc.lay.f64_total() * sizeof(double);
+    e = cudaFuncSetAttribute(selection_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, selection_kernel, 256, smem);
+  }
+  if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
 cudaError_t launch_selection(const SelArgs& a, cudaStream_t s) {
   if (a.fp_mode == CHB_FP32) {
     size_t smem32 = (size_t)(a.mc.lay.f32_total() - a.mc.lay.f32_dl4()) * sizeof(double);

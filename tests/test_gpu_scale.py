@@ -57,6 +57,18 @@ def test_c3_fp32_vs_fp64_and_oracle(cb, c3):
     assert _err(l32[0][j, :12], ref) < 1e-5
 
 
+def test_c3_all_units_fp32_vs_fp64(cb, c3):
+  """Every one of the 256 x 1000 (hyper-point, event) units of C3: fp32 mode against the fp64 mode of the same library
+  (which the test above holds to the oracle at 1e-9).  Budget of the fp32 mode: 1e-3; asserted: 1e-5."""
+  import bench
+  w, like = c3
+  l32 = like.compute_all(**w["hyper"])
+  l64 = bench.build_likelihood(w, "fp64").compute_all(**w["hyper"])
+  assert l32[0].shape == (256, 1000)
+  assert _err(l32[0], l64[0]) < 1e-5
+  np.testing.assert_allclose(l32[3], l64[3], rtol=1e-6)
+
+
 def test_c3_invariances(cb, c3):
   import bench
   w, like = c3
