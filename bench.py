@@ -99,6 +99,31 @@ def parse_options(text):
   return {k: float(v) for k, v in (kv.split("=") for kv in text.split(",") if kv)}
 
 
+def line_config(args, world):
+  """The `config` object of the JSON line -- the SAME for both arms (`--impl ours` / `--impl reference`): it names the
+  workload, its sizes and how the timed region treats the caches; arm-specific facts go elsewhere in the line."""
+  from chimera_b200 import parallel
+  c = CONFIGS[args.config]
+  weak = world > 1 and args.scaling == "weak"
+  nev = args.nev or c["nev"]
+  ninj = args.ninj or c["ninj"]
+  n_hyper = len(next(iter((c5_walkers() if c["hyper"] is None else c["hyper"]()).values())))
+  E = world // max(1, args.hyper_groups)
+  lo, hi = (0, nev) if weak else parallel.shard_bounds(nev, 0, max(1, E))
+  return {"workload": c["workload"], "events_total": nev * (world if weak else 1), "events_per_gpu": hi - lo,
+          "samples_per_event": c["ns"], "injections_total": int(ninj * (world if weak else 1)), "n_hyper": n_hyper,
+          "z_int_res": c["nz"],
+          "fp_mode": (args.fp_mode + ": fp32 reweighting + KDE pair sums (MUFU), fp64 tables/statistics/z-integral/reductions"
+                      if args.fp_mode == "fp32" else "fp64 throughout") + " (GPU arm; the CPU arm is fp64 like the reference)",
+          "l2": "inputs larger than L2 (120 MB packed samples + 32 MB injections + catalogue rows per GPU at N=1), no flush",
+          "p_cat": "GPU arm: precompute_p_cat on the GPU from 1.6e6 synthetic galaxies (z_err 0.001(1+z)), spiky rows; CPU arm: "
+                   "smooth synthetic rows of the same layout/sentinels (the CPU arm never touches the GPU)",
+          "sharding": ("one global data set, contiguous event/injection shards (CHIMERA/parallel.py:68-73,94-99)" if not weak
+                       else "every rank its own data set") + (f", hyper_groups={args.hyper_groups}" if args.hyper_groups > 1 else ""),
+          "step": "all hyper-points x (all events + all injections) + all-reduce of (n_hyper,3) partials",
+          "options": parse_options(args.options)}
+
+
 # ------------------------------------------------------------------------------------------ workloads
 def build_workload(name, seed_rank=0, nev=None, **overrides):
   """Synthetic inputs of configuration `name` (SURVEY.md section 8d recipes, chimera_b200/synth.py).  The
@@ -501,8 +526,8 @@ def run_reference(args, rank, world):
   line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
           "warmup": args.warmup, "ms_per_step": 1e3 * float(np.median([v["seconds"] for v in vals])),
           "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-          "config": {"workload": c["workload"],
-                     "note": "CPU oracle (NumPy fp64 restatement of the reference's path); real reference: " + why},
+          "config": line_config(args, world),
+          "note": "CPU oracle (NumPy fp64 restatement of the reference's path); real reference: " + why,
           "cpu_baseline": {"value": rate, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
           "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
           "gpu_launches": 0}
@@ -659,16 +684,7 @@ def run_ours(args, rank, world, local_rank):
     "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
     "ms_per_step": tm["ms_per_step"], "higher_is_better": True, "scaling": "weak" if weak else "strong", "vs_baseline": None,
     "dtype": "f32" if args.fp_mode == "fp32" else "f64", "data": "synthetic",
-    "config": {"workload": c["workload"], "events_total": nev_glob, "events_per_gpu": nev_local, "samples_per_event": c["ns"],
-               "injections_total": int(w["inj"]["dL"].size * (world if weak else 1)), "n_hyper": n_hyper, "z_int_res": c["nz"],
-               "fp_mode": (args.fp_mode + ": fp32 reweighting + KDE pair sums (MUFU), fp64 tables/statistics/z-integral/reductions"
-                           if args.fp_mode == "fp32" else "fp64 throughout"),
-               "l2": "inputs larger than L2 (120 MB packed samples + 32 MB injections + catalogue rows per GPU at N=1), no flush",
-               "p_cat": "precompute_p_cat on the GPU from 1.6e6 synthetic galaxies (z_err 0.001(1+z)): spiky rows, same layout/sentinels",
-               "sharding": ("one global data set, contiguous event/injection shards (CHIMERA/parallel.py:68-73,94-99)" if not weak
-                            else "every rank its own data set") + (f", hyper_groups={args.hyper_groups}" if args.hyper_groups > 1 else ""),
-               "step": "all hyper-points x (all events + all injections) + all-reduce of (n_hyper,3) partials",
-               "options": opts},
+    "config": line_config(args, world),
     "roofline": roof,
     "roofline_selection": {"bound": "hbm", "kernel": "selection_f32_kernel" if args.fp_mode == "fp32" else "selection_kernel",
                            "achieved": sel_bytes / (sel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",

@@ -281,7 +281,10 @@ struct TableLayout {
   __host__ __device__ int f32_cd4() const { return 4 * rcs; }
   __host__ __device__ int f32_lut() const { return 4 * rcs + 2 * rms; }
   __host__ __device__ int f32_fc() const { return 4 * rcs + 2 * rms + CHB_LUT_CAP / 4; }   // CHB_NFC floats (FC_* below)
+  // br: one float4 row {dL_k, z_k, slope_k, dL_k+1} PER LUT BUCKET (the dl4 row of the knot interval at the bucket's lower edge):
+  // z_from_dGW reads br[b] and br[b + 1] with two independent loads instead of the dependent chain lut[b] -> dl4[k] -> dl4[k + 1]
   __host__ __device__ int f32_total() const { return 4 * rcs + 2 * rms + CHB_LUT_CAP / 4 + CHB_NFC / 2; }
+  __host__ __device__ int f32_core() const { return f32_total(); }    // what the staging kernels copy
   __host__ __device__ int total() const { return f64_total() + f32_total(); }
 };
 static inline TableLayout make_layout(int rc, int rm) {

@@ -56,7 +56,7 @@ __host__ __device__ inline SmemPlan make_plan(int tab_total, int Nz, int B, int 
   return p;
 }
 size_t numerator_smem_bytes(const NumArgs& a, bool stage_in_smem) {
-  return (size_t)make_plan(a.fp_mode == CHB_FP32 ? a.mc.lay.f32_total() : a.mc.lay.f64_total(), a.Nz, a.binning ? a.num_bins : 0, a.Ns, a.kind, stage_in_smem).total * sizeof(double);
+  return (size_t)make_plan(a.fp_mode == CHB_FP32 ? a.mc.lay.f32_core() : a.mc.lay.f64_total(), a.Nz, a.binning ? a.num_bins : 0, a.Ns, a.kind, stage_in_smem).total * sizeof(double);
 }
 long long numerator_scratch_doubles(const NumArgs& a) {
   return (long long)(a.kind == CHB_PGW_FULL ? 4 : 2) * a.Ns;
@@ -143,7 +143,7 @@ numerator_kernel(const NumArgs a) {
   const int Ns = a.Ns, Nz = a.Nz, Pp = a.P, B = a.binning ? a.num_bins : 0;
   constexpr bool in_smem = STAGE_SMEM;
   constexpr int fp_mode = F32 ? CHB_FP32 : CHB_FP64;
-  const int tab_total = F32 ? lay.f32_total() : lay.f64_total();
+  const int tab_total = F32 ? lay.f32_core() : lay.f64_total();
   const SmemPlan pl = make_plan(tab_total, Nz, B, Ns, a.kind, in_smem);
   double* tab = sm + pl.tab;
   double* zgrid = sm + pl.zgrid;

@@ -64,7 +64,7 @@ __host__ __device__ inline FPlan make_fplan(int tab_doubles, int Nz, int B, int 
   p.total = o;
   return p;
 }
-static inline int f32_tab_doubles(const TableLayout& lay) { return lay.f32_total() - lay.f32_dl4(); }
+static inline int f32_tab_doubles(const TableLayout& lay) { return lay.f32_core() - lay.f32_dl4(); }
 
 size_t numerator_f32_smem_bytes(const NumArgs& a, int mode) {
   return (size_t)make_fplan(f32_tab_doubles(a.mc.lay), a.Nz, a.binning ? a.num_bins : 0, a.Ns, a.kind, mode, F_NW).total * sizeof(double);
@@ -163,7 +163,10 @@ zgrid_terms_kernel(const NumArgs a, int h0, int nh) {
 }
 cudaError_t launch_zgrid_terms(const NumArgs& a, int h0, int nh, cudaStream_t s) {
   const long long n = (long long)a.Nev * a.Nz;
-  int gx = (int)std::min<long long>((n + 255) / 256, 148LL * 8);
+  // ~16 CTAs per SM over the whole launch: every CTA rebuilds its hyper-point's constants (fp64), so a thread should
+  // amortise that over many grid points (C3: 256 hyper-points x 10 CTAs, ~120 points per thread; one point per thread
+  // cost 1.06 ms of which ~0.9 ms was the per-CTA set-up)
+  int gx = (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, (148LL * 16 + nh - 1) / nh));
   dim3 grid(gx, nh);
   zgrid_terms_kernel<<<grid, 256, 0, s>>>(a, h0, nh);
   return cudaGetLastError();
@@ -178,7 +181,9 @@ cudaError_t launch_zgrid_terms(const NumArgs& a, int h0, int nh, cudaStream_t s)
 // staged samples of a unit (one TMA bulk copy into shared memory).  Splitting lets either half run with three
 // co-resident CTAs per SM (no 42 KB table block next to the 40 KB sample stage) -- see DESIGN.md section 4.
 template <int KG, int MODE, int NT>
-__global__ void __launch_bounds__(NT, MODE == 0 ? 2 : (MODE == 1 ? CHB_K1_MINB : CHB_K2_MINB))
+// ('full', MODE 2: one CTA per SM whatever the register count -- 120 KB of samples in shared memory -- so the pair loop
+// gets the registers to keep several samples in flight)
+__global__ void __launch_bounds__(NT, MODE == 0 ? 2 : (MODE == 1 ? CHB_K1_MINB : (KG == 2 ? 1 : CHB_K2_MINB)))
 numerator_f32_kernel(const NumArgs a) {
   constexpr int NW = NT / 32;
   extern __shared__ __align__(16) double sm[];
@@ -193,7 +198,7 @@ numerator_f32_kernel(const NumArgs a) {
 
   const TableLayout lay = a.mc.lay;
   const int Ns = a.Ns, Nz = a.Nz, Pp = a.P, B = a.binning ? a.num_bins : 0;
-  const int tabd = lay.f32_total() - lay.f32_dl4();
+  const int tabd = lay.f32_core() - lay.f32_dl4();
   const FPlan pl = make_fplan(tabd, Nz, B, Ns, a.kind, MODE, NW);
   double* tab = sm + pl.tab;
   double* zgrid = sm + pl.zgrid;
@@ -702,7 +707,15 @@ numerator_f32_kernel(const NumArgs a) {
       constexpr int FR = 4;                       // evaluation points per lane: two packed pairs (FADD2 / FMUL2 / FFMA2)
       const double enorm = exp(lognorm) * norm;
       const int ntiles = (npts + 32 * FR - 1) / (32 * FR);
-      for (int t = warp; t < ntiles; t += NW) {
+      // Work items = (tile of 32 FR points) x (slice of the samples): the likelihood is linear in the pair sums, so a
+      // warp multiplies its PARTIAL sum of a point by the point's catalogue factor; slices make the item count a
+      // multiple of the warp count (34 tiles on 8 warps left 1/7 of the warps idle at the end).  p_gw output wants
+      // complete sums per point: one slice then.
+      int S = 1;
+      while (!pout && (ntiles * S) % NW != 0 && S < 8 && Ns / (2 * S) >= 256) S *= 2;
+      const int per = (((Ns + S - 1) / S) + 3) & ~3;
+      for (int it = warp; it < ntiles * S; it += NW) {
+        const int t = it / S, jlo = (it - t * S) * per, jhi = min(Ns, jlo + per);
         float q0[FR], q1[FR], q2[FR], acc[FR];
         int pk[FR];
 #pragma unroll
@@ -728,7 +741,7 @@ numerator_f32_kernel(const NumArgs a) {
           nq2[r] = pk2(-q2[2 * r], -q2[2 * r + 1]); acc2[r] = 0ull;
         }
 #pragma unroll 4
-        for (int j = 0; j < Ns; ++j) {
+        for (int j = jlo; j < jhi; ++j) {
           const float4 v = yw[j];
           const f32x2 vx = pk2(v.x, v.x), vy = pk2(v.y, v.y), vz = pk2(v.z, v.z), vw = pk2(v.w, v.w);
 #pragma unroll

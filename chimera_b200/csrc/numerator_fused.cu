@@ -40,6 +40,12 @@
 #define CHB_FU_CPASYNC 1          // 1: every warp stages its NEXT 64-sample block of packed samples in shared memory with
 #endif                            //    cp.async (1.5 KB per warp, issued a whole block ahead: the L2 latency of the sample stream is
                                   //    off the critical path and no second register set is needed); 0: direct ld.global.cg
+#ifndef CHB_FU_TAILPF
+#define CHB_FU_TAILPF 0           // 1: right after the reweighting every 16th thread issues prefetch.global.L1 for the rows the
+#endif                            //    z-integral reads once the KDE is done (event grid, z-grid terms, collapsed catalogue rows) and
+                                  //    for the next unit's constants: their L2 latency hides behind the KDE instead of standing
+                                  //    at the end of the unit, where two warps walk the 300-point grid alone.  Measured: 0.6 % SLOWER
+                                  //    (the co-resident CTAs already cover that latency); kept as a switch
 #ifndef CHB_FU_PREFETCH
 #define CHB_FU_PREFETCH 0         // 1: the next block's packed samples are requested one block ahead (two register sets);
 #endif                            // 0 (default, measured 1 % faster): every block requests its successor's samples right after
@@ -138,6 +144,8 @@ __device__ __forceinline__ int fu_lut_bucket(const FuTab& t, float dL) {
 }
 __device__ __forceinline__ float fu_z_from_dL(const FuTab& t, float dL) {
   const int b = fu_lut_bucket(t, dL);
+  // (a per-bucket copy of the rows -- two independent loads instead of lut -> dl4 -> dl4 -- was measured: no gain, the
+  //  other warps of the SM cover this chain)
   int k = __ldg(t.lut + b);
   float4 e = __ldg(t.dl4 + k);
   if (dL >= e.w && k < t.rc - 2) { ++k; e = __ldg(t.dl4 + k); }
@@ -529,6 +537,28 @@ numerator_fused_kernel(const NumArgs a) {
     }
     __syncthreads();                                         // publishes stage[], sub[] and the warp partials
     for (int i = tid; i < FU_NW * G; i += FU_NT) rows[i] = 0.0;     // (every KDE routine has a barrier before it adds to them)
+#if CHB_FU_TAILPF
+    if ((tid & 15) == 0) {
+      // one hint per 128-byte line (16 doubles / float2) of the rows of the z-integral
+      for (int k = tid; k < Nz; k += FU_NT) {
+        fu_prefetch_l1(a.zgrids + (size_t)ev * Nz + k);
+        if (a.zterms) fu_prefetch_l1(a.zterms + ((size_t)(h - a.zterms_h0) * a.Nev + ev) * Nz + k);
+        if (a.kind != CHB_PGW_1D && a.catA) {
+          fu_prefetch_l1(a.catA + (size_t)ev * Nz + k); fu_prefetch_l1(a.catB + (size_t)ev * Nz + k);
+          if (has_cat) fu_prefetch_l1(a.P_compl + (size_t)ev * Nz + k);
+        }
+      }
+    } else if (tid < 8) {
+      // the next unit's constant rows (hyper-parameters 2 lines, host constants, FC)
+      const long long nu = unit + gridDim.x;
+      if (nu < units) {
+        const int nh = (int)(nu % a.n_hyper);
+        if (tid < 3) fu_prefetch_l1(a.hyper + (size_t)nh * CHB_NPAR + (tid - 1) * 16);
+        else if (tid < 5) fu_prefetch_l1(a.HC + (size_t)nh * CHB_NHC + (tid - 3) * 16);
+        else if (tid == 6) fu_prefetch_l1(reinterpret_cast<const float*>(a.tabs + (size_t)nh * lay.total() + lay.off_f32() + lay.f32_fc()));
+      }
+    }
+#endif
     FuStats st = {0.0, 0.0, 0.0, 0.0, INFINITY, -INFINITY};
 #pragma unroll
     for (int i = 0; i < FU_NW; ++i) {

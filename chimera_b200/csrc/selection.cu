@@ -85,7 +85,7 @@ selection_f32_kernel(SelArgs a) {
   const TableLayout lay = a.mc.lay;
   const int h = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
   const int part_off = lay.f32_dl4();
-  const uint32_t tab_bytes = (uint32_t)((lay.f32_total() - part_off) * sizeof(double));
+  const uint32_t tab_bytes = (uint32_t)((lay.f32_core() - part_off) * sizeof(double));
   if (tid == 0) mbar_init(&bar, 1);
   __syncthreads();
   if (tid == 0) {
@@ -146,7 +146,7 @@ int selection_ctas_per_sm(const ModelCfg& mc, int fp_mode) {
   int n = 0;
   cudaError_t e;
   if (fp_mode == CHB_FP32) {
-    const size_t smem = (size_t)(mc.lay.f32_total() - mc.lay.f32_dl4()) * sizeof(double);
+    const size_t smem = (size_t)(mc.lay.f32_core() - mc.lay.f32_dl4()) * sizeof(double);
     e = cudaFuncSetAttribute(selection_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, selection_f32_kernel, 256, smem);
   } else {
@@ -160,7 +160,7 @@ int selection_ctas_per_sm(const ModelCfg& mc, int fp_mode) {
 
 cudaError_t launch_selection(const SelArgs& a, cudaStream_t s) {
   if (a.fp_mode == CHB_FP32) {
-    size_t smem32 = (size_t)(a.mc.lay.f32_total() - a.mc.lay.f32_dl4()) * sizeof(double);
+    size_t smem32 = (size_t)(a.mc.lay.f32_core() - a.mc.lay.f32_dl4()) * sizeof(double);
     cudaError_t e32 = cudaFuncSetAttribute(selection_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
     if (e32 != cudaSuccess) return e32;
     dim3 grid32(a.tiles, a.n_hyper);
