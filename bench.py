@@ -92,6 +92,8 @@ def parse():
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--options", default="", help="per-handle tuning switches for A/B runs, e.g. 'fused=0,kde_win=0' (chb_set_option)")
   ap.add_argument("--hyper-groups", type=int, default=1)
+  ap.add_argument("--kde", default="", help="profiling runs: 'epan-binned' evaluates the configuration with the reference's default "
+                  "KDE options (kernel='epan', binning=True); needs --no-cpu-baseline")
   return ap.parse_args()
 
 
@@ -600,7 +602,8 @@ def run_ours(args, rank, world, local_rank):
   w = build_workload(name, seed_rank=rank if weak else 0, nev=args.nev or None, **({"ninj": args.ninj} if args.ninj else {}))
   torch.cuda.synchronize()
   t_cold = time.perf_counter()
-  like = build_likelihood(w, args.fp_mode, distributed=world > 1, presharded=weak, options=opts, hyper_groups=args.hyper_groups)
+  kov = {"epan-binned": dict(kernel="epan", binning=True), "epan": dict(kernel="epan", binning=False)}.get(args.kde, {})
+  like = build_likelihood(w, args.fp_mode, distributed=world > 1, presharded=weak, options=opts, hyper_groups=args.hyper_groups, **kov)
   like(**w["hyper"])
   torch.cuda.synchronize()
   cold_s = time.perf_counter() - t_cold
@@ -654,11 +657,11 @@ def run_ours(args, rank, world, local_rank):
   sm_mhz = clocks.get("sm_mhz") or sm_max
   hbm_peak, hbm_src = measured_peaks()
   km = tm["kernel_ms"]
-  roof = kde_roofline(w, tm, args.fp_mode, float(peak[0]), clocks, nev_local=nev_local)
+  roof = kde_roofline(w, tm, args.fp_mode, float(peak[0]), clocks, nev_local=nev_local, binning=kov.get("binning"))
   roof["nominal_peak"] = 148 * 16 * sm_max * 1e6 / 1e9
   prof = executed_profile()
   roof_exec = None
-  same_cmd = prof and prof.get("config") == name and prof.get("fp_mode") == args.fp_mode and not args.options
+  same_cmd = prof and prof.get("config") == name and prof.get("fp_mode") == args.fp_mode and not args.options and not args.kde
   if same_cmd:
     # executed work: warp instructions of the capture per unit x units of this run / measured kernel time, against the
     # issue rate 148 SMs x 4 schedulers x f_SM (the clock sampled during THIS run); the MUFU fraction likewise
@@ -722,7 +725,7 @@ def run_ours(args, rank, world, local_rank):
     line["parity_check"] = {"max_err_vs_oracle": float(np.max(np.abs(lle[fin] - ref[fin]) / np.maximum(np.abs(ref[fin]), 1.0))),
                             "metric": "|d log L| / max(|log L|, 1) per (event, hyper-point)", "units": int(fin.sum())}
   elif world == 1:
-    line["parity_check"] = parity_check(w, like, 16, 4, procs=min(os.cpu_count() or 1, 8))
+    line["parity_check"] = parity_check(w, like, 16, 4, procs=min(os.cpu_count() or 1, 8), **kov)
   lle32_all = None
   if world == 1 and "C3_fp64" in subs and args.fp_mode == "fp32":
     lle32_all = like.compute_all(**w["hyper"])[0]

@@ -76,6 +76,7 @@ struct chb_handle {
   double opt_kde_win_t2 = 24.0;            // window threshold in bits (fused kernel)
   int opt_kde_direct = 0;                  // 1: one MUFU.EX2 per pair (no recurrence)
   int opt_bin_runs = 1;                    // round-1 path: binning by runs of the sorted samples
+  int opt_epan_blocks = 1;                 // fused kernel, unbinned Epanechnikov: block moments (0: direct pair sums)
   double opt_stage_gb = 12.0;              // round-1 path: budget of the {z, w} stage buffer
   DevBuf<double> catA, catB;
   bool cat_collapsed = false;
@@ -388,7 +389,7 @@ static int eval_impl(chb_handle* h, int64_t n_hyper, const double* d_hyper, doub
     a.kind = c.kind_p_gw; a.kernel = c.kernel; a.bw_method = c.bw_method; a.use_cut = c.use_cut_grid;
     a.binning = (c.kind_p_gw == CHB_PGW_FULL) ? 0 : c.binning; a.num_bins = c.num_bins; a.fp_mode = c.fp_mode;
     a.bw_value = c.bw_value; a.cut_grid = c.cut_grid; a.pe_neff = c.pe_neff;
-    a.rec_off = h->opt_kde_direct; a.bin_runs = h->opt_bin_runs;
+    a.rec_off = h->opt_kde_direct; a.bin_runs = h->opt_bin_runs; a.epan_blocks = h->opt_epan_blocks;
     a.kde_win_iters = h->sorted ? h->opt_kde_win : 0;
     a.win_t2 = (float)h->opt_kde_win_t2;
     a.Nev = (int)h->Nev; a.Ns = (int)h->Ns; a.Nz = (int)h->Nz; a.P = (int)std::max<int64_t>(h->P, 1);
@@ -599,6 +600,7 @@ int chb_set_option(chb_handle* h, const char* name, double value) {
   else if (n == "kde_win_t2") { if (!(value >= 16.0 && value <= 60.0)) return fail(h, CHB_ERR_INVALID, "kde_win_t2 must be in [16, 60]"); h->opt_kde_win_t2 = value; }
   else if (n == "kde_direct") h->opt_kde_direct = value != 0.0;
   else if (n == "bin_runs") h->opt_bin_runs = value != 0.0;
+  else if (n == "epan_blocks") h->opt_epan_blocks = value != 0.0;
   else if (n == "stage_gb") { if (!(value > 0.0)) return fail(h, CHB_ERR_INVALID, "stage_gb must be positive"); h->opt_stage_gb = value; }
   else return fail(h, CHB_ERR_INVALID, "unknown option '" + n + "'");
   h->plan_nh = -1; h->fused_per = -1; h->marg_per = -1;

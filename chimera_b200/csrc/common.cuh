@@ -17,6 +17,7 @@ struct NumArgs {
   int kind, kernel, bw_method, use_cut, binning, num_bins, fp_mode;
   int rec_off;           // 1: disable the Gaussian recurrence (one MUFU.EX2 per pair), env CHB_KDE_DIRECT=1
   int bin_runs;          // 1: binning1d by contiguous runs of the sorted samples (default; env CHB_BIN_RUNS=0 restores one atomic per sample)
+  int epan_blocks;       // 1 (default): unbinned Epanechnikov KDE by block moments of the sorted samples (option epan_blocks; 0: direct pair sums)
   float win_t2;          // window threshold of the windowed KDE in bits (option kde_win_t2): terms below 2^-t2 of the largest term at a grid point are dropped
   int kde_win_iters;     // > 0: windowed recurrence over sorted samples, sub-stream iterations per chunk (env CHB_KDE_WIN, default 32; 0 = off)
   double bw_value, cut_grid, pe_neff;

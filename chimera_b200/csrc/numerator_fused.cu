@@ -406,6 +406,64 @@ __device__ __noinline__ void fu_direct(const float4* __restrict__ pairs, int npa
   }
 }
 
+// ---- Epanechnikov KDE of the staged samples WITHOUT binning (utils/math.py:52-85, kernel 'epan') ---------------------------
+// The kernel has compact support, |g - x| <= 1 in units of the bandwidth, and the samples are sorted, so for a grid point
+// almost every 64-sample block lies entirely inside or entirely outside the support:
+//     inside:   sum_j w_j (1 - (g - x_j)^2) = (1 - D^2) M0 + 2 D M1 - M2,   D = g - c_b,  M_k = sum_j w_j (x_j - c_b)^k
+//               about the block's own centre c_b (|D| <= 1 and a narrow block: nothing cancels in fp32);
+//     outside:  skipped;      straddling the edge of the support (two blocks per grid point, more in sparse tails): summed directly.
+// O(Ns + G Ns / 64) instead of the O(G Ns) pair sums.  The classification uses the block's hull {min x, max x}, so the
+// result does not depend on the samples actually being sorted -- only the cost does.
+// blk: 8 floats per block {lo, hi, c, M0, M1, M2, -, -} (the per-warp rows are idle in this path).  Whole-CTA call; ends
+// with dens[] written (no barrier after).
+__device__ __noinline__ void fu_epan_blocks(const float4* __restrict__ pairs, int npairs, int G, double gfirst, double hd,
+                                            float sf, double scale, float* __restrict__ blk, double* __restrict__ dens) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nblk = (npairs + 31) / 32;
+  for (int b = warp; b < nblk; b += FU_NW) {
+    const int j = b * 32 + lane;
+    const bool on = j < npairs;
+    const float4 v = on ? pairs[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float xa = v.x * sf, xb = v.y * sf;
+    const float lo = warp_min_f32(on ? fminf(xa, xb) : INFINITY), hi = warp_max_f32(on ? fmaxf(xa, xb) : -INFINITY);
+    const float c = 0.5f * (lo + hi);
+    const float da = xa - c, db = xb - c;
+    float m0 = v.z + v.w, m1 = fmaf(v.z, da, v.w * db), m2 = fmaf(v.z * da, da, v.w * db * db);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      m0 += __shfl_xor_sync(0xffffffffu, m0, o); m1 += __shfl_xor_sync(0xffffffffu, m1, o); m2 += __shfl_xor_sync(0xffffffffu, m2, o);
+    }
+    if (lane == 0) {
+      reinterpret_cast<float4*>(blk)[2 * b] = make_float4(lo, hi, c, m0);
+      reinterpret_cast<float4*>(blk)[2 * b + 1] = make_float4(m1, m2, 0.f, 0.f);
+    }
+  }
+  __syncthreads();
+  for (int g = tid; g < G; g += FU_NT) {
+    const float gp = (float)(gfirst + (double)g * hd);
+    const float glo = gp - 1.f, ghi = gp + 1.f;
+    float acc = 0.f;
+    for (int b = 0; b < nblk; ++b) {
+      const float4 h4 = reinterpret_cast<const float4*>(blk)[2 * b];
+      if (h4.y < glo || h4.x > ghi) continue;                  // (a NaN hull fails both tests and is summed directly)
+      if (h4.x >= glo && h4.y <= ghi) {
+        const float4 m4 = reinterpret_cast<const float4*>(blk)[2 * b + 1];
+        const float D = gp - h4.z;
+        acc += fmaf(fmaf(-D, D, 1.f), h4.w, fmaf(2.f * D, m4.x, -m4.y));
+      } else {
+        const int j1 = min(npairs, b * 32 + 32);
+        for (int j = b * 32; j < j1; ++j) {
+          const float4 v = pairs[j];
+          const float da = gp - v.x * sf, db = gp - v.y * sf;
+          acc = fmaf(v.z, fmaxf(fmaf(-da, da, 1.f), 0.f), acc);
+          acc = fmaf(v.w, fmaxf(fmaf(-db, db, 1.f), 0.f), acc);
+        }
+      }
+    }
+    dens[g] = (double)acc * scale;
+  }
+}
+
 // ---- Epanechnikov KDE of B equally spaced bin centres by prefix sums (utils/math.py:32-46 + 52-85) -------------------
 // kde1d with the compact kernel K(u) = 3/4 (1 - u^2) [|u| <= 1] over bin centres c_b = first + b * bstep with weights
 // w_b: the bins inside the support of a grid point form a contiguous index range, so
@@ -520,6 +578,9 @@ numerator_fused_kernel(const NumArgs a) {
   for (long long unit = blockIdx.x; unit < units; unit += gridDim.x) {
     const int ev = (int)(unit / a.n_hyper), h = (int)(unit % a.n_hyper);
     const double* tblk = a.tabs + (size_t)h * lay.total() + lay.off_f32();
+    // (measured, round 2: double-buffering these constants with cp.async, deferring the unit's final sum/log to the next unit
+    //  and two grid points per thread-round in the z-integral removed two barriers per unit but cost registers: C3 +-0,
+    //  C1 and the binned path 3-4 % slower -- not adopted)
     __syncthreads();                                         // the previous unit is done with every shared array
     if (tid < CHB_NPAR) P[tid] = a.hyper[(size_t)h * CHB_NPAR + tid];
     else if (tid >= 64 && tid < 64 + CHB_NHC) HC[tid - 64] = a.HC[(size_t)h * CHB_NHC + tid - 64];
@@ -606,6 +667,8 @@ numerator_fused_kernel(const NumArgs a) {
       if (windowed) {
         fu_kde_win(stage, Ns, G, gfirst, hd, wp.R, wp.LPS, wp.chunk, wp.nchunks, scale, sf, -lg2f_((float)s1), a.win_t2, sub, summ, win,
                    cr, rows, dens);
+      } else if (!gauss && a.epan_blocks) {
+        fu_epan_blocks(stage, Ns / 2, G, gfirst, hd, sf, scale / s1, reinterpret_cast<float*>(rows), dens);
       } else {
         const float koff = gauss ? -lg2f_((float)s1) : 0.f;
         fu_direct(stage, Ns / 2, G, gfirst, hd, sf, koff, gauss, gauss ? scale : scale / s1, rows, dens);
@@ -651,8 +714,10 @@ numerator_fused_kernel(const NumArgs a) {
       const double dstd = sqrt(fmax(u.d / B - cmean * cmean, 0.0));   // std of the BIN CENTRES (math.py:67 on binning1d's output)
       const double neff_k = 1.0 / (Q / (W * W));
       double bw;
-      if (a.bw_method == CHB_BW_SCOTT) bw = pow(neff_k, -0.2) * dstd;
-      else if (a.bw_method == CHB_BW_SILVERMAN) bw = pow(neff_k * 3.0 / 4.0, -0.2) * dstd;
+      // (n^-1/5 through MUFU lg2/ex2 like the unbinned branch: ~1e-6 relative on the bandwidth, the fp32 mode's own level,
+      //  instead of ~200 fp64 instructions of pow() per thread)
+      if (a.bw_method == CHB_BW_SCOTT) bw = (double)ex2f_(-0.2f * lg2f_((float)neff_k)) * dstd;
+      else if (a.bw_method == CHB_BW_SILVERMAN) bw = (double)ex2f_(-0.2f * lg2f_((float)(neff_k * 3.0 / 4.0))) * dstd;
       else bw = a.bw_value * dstd;
       if (!gauss) {
         // Epanechnikov (the reference's default kernel): prefix sums over the bins, O(1) per grid point
@@ -884,8 +949,10 @@ numerator_marg_kernel(const NumArgs a) {
       const double dstd = sqrt(fmax(sc2 / B - cmean * cmean, 0.0));
       const double neff_k = 1.0 / (Q / (W * W));
       double bw;
-      if (a.bw_method == CHB_BW_SCOTT) bw = pow(neff_k, -0.2) * dstd;
-      else if (a.bw_method == CHB_BW_SILVERMAN) bw = pow(neff_k * 3.0 / 4.0, -0.2) * dstd;
+      // (n^-1/5 through MUFU lg2/ex2 like the unbinned branch: ~1e-6 relative on the bandwidth, the fp32 mode's own level,
+      //  instead of ~200 fp64 instructions of pow() per thread)
+      if (a.bw_method == CHB_BW_SCOTT) bw = (double)ex2f_(-0.2f * lg2f_((float)neff_k)) * dstd;
+      else if (a.bw_method == CHB_BW_SILVERMAN) bw = (double)ex2f_(-0.2f * lg2f_((float)(neff_k * 3.0 / 4.0))) * dstd;
       else bw = a.bw_value * dstd;
       // W == 0 (no weight in the pixel) -> w/W = NaN for every sample in the reference
       const double scale = (W != 0.0) ? norm * gwp[p] * 0.75 / bw : nan("");

@@ -117,6 +117,7 @@ void chb_destroy(chb_handle* h);
  *                point are dropped (fp32 carries 24 bits); 30 was round 1's setting
  *   "kde_direct" 0 (default) | 1: one MUFU.EX2 per (grid point, sample) pair, no recurrence
  *   "bin_runs"   1 (default) | 0: non-fused binning by runs of sorted samples | one shared-memory atomic per sample
+ *   "epan_blocks" 1 (default) | 0: fused kernel, unbinned Epanechnikov KDE by block moments of the sorted samples | direct pair sums
  *   "stage_gb"   12 (default): budget of the stage buffer of the non-fused form; hyper-points are batched beyond it
  * Unknown names / out-of-range values: CHB_ERR_INVALID. */
 int chb_set_option(chb_handle* h, const char* name, double value);

@@ -74,10 +74,36 @@ def test_fused_kernel_kde_options(cb, kernel, binning, bw):
   pop0 = orc.make_pop(orc.make_cosmo("flrw", z_max=5.), orc.make_mass("plp"), orc.make_rate("madau_dickinson"))
   opts = orc.make_opts(None, kernel, bw, 2.0, binning, 200, 2.0)
   ref = np.array([orc.compute_all(pop0, ev, zg, opts, inj, N_inj, 5., None, H0=float(h))[0] for h in H0])
-  for opt in ({}, {"fused": 0}):
+  for opt in ({}, {"fused": 0}, {"epan_blocks": 0}):
     like = cb.hyperlikelihood(th, zg, pop, sel, kernel=kernel, bw_method=bw, binning=binning, num_bins=200,
                               fp_mode="fp32", options=opt)
     _check(like.compute_all(H0=H0)[0], ref, tol=1e-4)
+
+
+@pytest.mark.parametrize("bw,ns", [(None, 4096), ("silverman", 5000), (0.3, 700), (0.05, 4096)])
+def test_epanechnikov_unbinned_block_moments(cb, bw, ns):
+  """Unbinned Epanechnikov KDE of the fused kernel (block moments of the sorted samples, fu_epan_blocks) against the
+  oracle's pair sums and against the direct pair sums of the same kernel (`epan_blocks=0`); wide and narrow bandwidths,
+  a ragged last block."""
+  from oracle import chimera_oracle as orc
+  from chimera_b200 import synth
+  nev = 8
+  ev = synth.make_events(nev, ns, seed=451, sky=False)
+  zg = synth.make_z_grids(ev["dL"], z_int_res=300, H0_prior=(40., 120.))
+  inj, N_inj = synth.make_injections(20000, seed=452)
+  th = cb.theta_pe_det(**{k: ev[k] for k in ("m1det", "m2det", "dL", "pe_prior")})
+  sel = cb.selection_function(cb.theta_inj_det(**inj), N_inj, 5.)
+  pop = cb.population(cb.cosmo.flrw(z_max=5.), cb.mass.plp(), cb.rate.madau_dickinson())
+  pop0 = orc.make_pop(orc.make_cosmo("flrw", z_max=5.), orc.make_mass("plp"), orc.make_rate("madau_dickinson"))
+  opts = orc.make_opts(None, "epan", bw, 2.0, False, 200, 2.0)
+  H0 = np.array([55., 70., 88.])
+  ref = np.array([orc.compute_all(pop0, ev, zg, opts, inj, N_inj, 5., None, H0=float(h))[0] for h in H0])
+  out = {}
+  for name, opt in (("blocks", {}), ("direct", {"epan_blocks": 0})):
+    like = cb.hyperlikelihood(th, zg, pop, sel, kernel="epan", bw_method=bw, binning=False, fp_mode="fp32", options=opt)
+    out[name] = like.compute_all(H0=H0)[0]
+    _check(out[name], ref, tol=2e-5)
+  _check(out["blocks"], out["direct"], tol=5e-6)
 
 
 def test_two_handles_interleaved(cb):
