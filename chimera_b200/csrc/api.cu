@@ -77,6 +77,7 @@ struct chb_handle {
   int opt_kde_direct = 0;                  // 1: one MUFU.EX2 per pair (no recurrence)
   int opt_bin_runs = 1;                    // round-1 path: binning by runs of the sorted samples
   int opt_epan_blocks = 1;                 // fused kernel, unbinned Epanechnikov: block moments (0: direct pair sums)
+  double opt_zterms_gb = 16.0;             // budget of the z-grid-term buffer; the one-launch kernels batch the hyper-points beyond it
   double opt_stage_gb = 12.0;              // round-1 path: budget of the {z, w} stage buffer
   DevBuf<double> catA, catB;
   bool cat_collapsed = false;
@@ -475,28 +476,58 @@ static int eval_impl(chb_handle* h, int64_t n_hyper, const double* d_hyper, doub
         // quarter of the free memory; otherwise the numerator kernels evaluate them in place)
         const size_t zt_elems = (size_t)n_hyper * h->Nev * h->Nz;
         a.zterms = nullptr; a.zterms_out = nullptr; a.zterms_h0 = 0;
-        bool zt_fit = zt_elems * sizeof(float2) <= ((size_t)2 << 30);
-        if (!zt_fit && zt_elems * sizeof(float2) <= ((size_t)16 << 30)) {
-          if (h->zterms.n >= zt_elems) zt_fit = true;
-          else { size_t free_b = 0, total_b = 0; cudaMemGetInfo(&free_b, &total_b); zt_fit = zt_elems * sizeof(float2) <= free_b / 4; }
+        bool zt_fit = zt_elems * sizeof(float2) <= std::min<size_t>((size_t)2 << 30, (size_t)(h->opt_zterms_gb * (double)((size_t)1 << 30)));
+        size_t zt_budget = (size_t)(h->opt_zterms_gb * (double)((size_t)1 << 30));
+        if (!zt_fit) {
+          size_t free_b = 0, total_b = 0;
+          cudaMemGetInfo(&free_b, &total_b);
+          zt_budget = std::min(zt_budget, std::max(free_b / 4, h->zterms.n * sizeof(float2)));
+          zt_fit = zt_elems * sizeof(float2) <= zt_budget;
+        }
+        // the one-launch kernels (fused / 'marginalized') take the hyper-points in batches whose z-grid terms fit the
+        // budget (large walker batches: C5 on one GPU is 98 GB of terms) -- always the precomputed terms, never the
+        // in-kernel evaluation
+        const size_t zt_per_h = (size_t)h->Nev * h->Nz;
+        int64_t zb = n_hyper;
+        if (!zt_fit && (fused || marg)) {
+          zb = std::max<int64_t>(1, (int64_t)(zt_budget / (zt_per_h * sizeof(float2))));
+          zt_fit = zt_per_h * sizeof(float2) <= zt_budget;
         }
         if (zt_fit) {
-          CU(h->zterms.alloc(zt_elems), "alloc z-grid terms");
+          CU(h->zterms.alloc((size_t)std::min<int64_t>(zb, n_hyper) * zt_per_h), "alloc z-grid terms");
           a.zterms_out = h->zterms.p;
+          a.zterms = h->zterms.p;
+        }
+        if (zt_fit && !(fused || marg)) {
           CU(launch_zgrid_terms(a, 0, (int)n_hyper, s), "zgrid_terms launch");
           h->launches++;
-          a.zterms = h->zterms.p;
           cudaEventRecord(h->evz, s);
         }
-        if (fused) {
-          const int grid = (int)std::min<long long>(units, (long long)h->sm_count * h->fused_per);
-          h->num_grid = grid; h->num_smem = ff;
-          CU(launch_numerator_fused(a, grid, ff, s), "numerator_fused launch");
-          fast = true;
-        } else if (marg) {
-          const int grid = (int)std::min<long long>(units, (long long)h->sm_count * h->marg_per);
-          h->num_grid = grid; h->num_smem = fm;
-          CU(launch_numerator_marg(a, grid, fm, s), "numerator_marg launch");
+        if (fused || marg) {
+          const int per = fused ? h->fused_per : h->marg_per;
+          const size_t smem = fused ? ff : fm;
+          h->num_smem = smem;
+          bool first = true;
+          for (int64_t h0 = 0; h0 < n_hyper; h0 += zb) {
+            const int64_t nh = std::min<int64_t>(zb, n_hyper - h0);
+            if (zt_fit) {
+              CU(launch_zgrid_terms(a, (int)h0, (int)nh, s), "zgrid_terms launch");
+              h->launches++;
+              if (first) cudaEventRecord(h->evz, s);      // (timings: the first batch's terms; later batches count as numerator)
+            }
+            NumArgs b = a;                         // this batch: pointers shifted to hyper-point h0
+            b.n_hyper = (int)nh;
+            b.hyper = a.hyper + (size_t)h0 * CHB_NPAR; b.tabs = a.tabs + (size_t)h0 * a.mc.lay.total(); b.HC = a.HC + (size_t)h0 * CHB_NHC;
+            b.log_like = a.log_like + (size_t)h0 * h->Nev; b.like_raw = a.like_raw + (size_t)h0 * h->Nev;
+            if (a.p_gw_out) b.p_gw_out = a.p_gw_out + (size_t)h0 * h->Nev * (size_t)(c.kind_p_gw == CHB_PGW_1D ? 1 : a.P) * h->Nz;
+            const long long ub = (long long)h->Nev * nh;
+            const int grid = (int)std::min<long long>(ub, (long long)h->sm_count * per);
+            h->num_grid = grid;
+            if (fused) { CU(launch_numerator_fused(b, grid, smem, s), "numerator_fused launch"); }
+            else { CU(launch_numerator_marg(b, grid, smem, s), "numerator_marg launch"); }
+            if (!first) h->launches++;             // the common `launches++` below counts the first one
+            first = false;
+          }
           fast = true;
         } else if (split) {
           const int per1 = h->plan_per1, per2 = h->plan_per2;
@@ -601,6 +632,7 @@ int chb_set_option(chb_handle* h, const char* name, double value) {
   else if (n == "kde_direct") h->opt_kde_direct = value != 0.0;
   else if (n == "bin_runs") h->opt_bin_runs = value != 0.0;
   else if (n == "epan_blocks") h->opt_epan_blocks = value != 0.0;
+  else if (n == "zterms_gb") { if (!(value > 0.0)) return fail(h, CHB_ERR_INVALID, "zterms_gb must be positive"); h->opt_zterms_gb = value; }
   else if (n == "stage_gb") { if (!(value > 0.0)) return fail(h, CHB_ERR_INVALID, "stage_gb must be positive"); h->opt_stage_gb = value; }
   else return fail(h, CHB_ERR_INVALID, "unknown option '" + n + "'");
   h->plan_nh = -1; h->fused_per = -1; h->marg_per = -1;

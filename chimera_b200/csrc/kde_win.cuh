@@ -89,10 +89,15 @@ __device__ __forceinline__ bool win_plan(int G, int n, float h, int iters, int m
   }
   if (pl.R == 0) return false;
   // at most 32 chunks (phase B keeps one chunk per lane), each a multiple of 4 sub-stream rounds
+  // Few samples (walker batches with ~1000 samples per event): shorter chunks rather than no windows at all -- the
+  // direct sums cost one MUFU per pair on the whole grid, ~4x the windowed recurrence even with 4 loop iterations per pass.
   const int q = 4 * (32 / pl.LPS);
-  pl.chunk = max(iters * (32 / pl.LPS), ((n + 31) / 32 + q - 1) / q * q);
-  pl.chunk = (pl.chunk + gran - 1) / gran * gran;
-  pl.nchunks = (n + pl.chunk - 1) / pl.chunk;
+  for (int it = iters;; it >>= 1) {
+    pl.chunk = max(it * (32 / pl.LPS), ((n + 31) / 32 + q - 1) / q * q);
+    pl.chunk = (pl.chunk + gran - 1) / gran * gran;
+    pl.nchunks = (n + pl.chunk - 1) / pl.chunk;
+    if (pl.nchunks >= 8 || it <= 8) break;
+  }
   (void)max_chunks;
   return pl.nchunks >= 8;
 }

@@ -439,20 +439,33 @@ __device__ __noinline__ void fu_epan_blocks(const float4* __restrict__ pairs, in
     }
   }
   __syncthreads();
-  for (int g = tid; g < G; g += FU_NT) {
+  // One grid point per warp and pass: the lanes classify the blocks (32 per round); a block inside the support adds its
+  // moment form on the lane that owns it, the blocks straddling the support's edge are then summed by the WHOLE warp
+  // (one pair per lane), and one shuffle reduction closes the grid point -- no lane ever walks a block alone.
+  const float4* __restrict__ blk4 = reinterpret_cast<const float4*>(blk);
+  for (int g = warp; g < G; g += FU_NW) {
     const float gp = (float)(gfirst + (double)g * hd);
     const float glo = gp - 1.f, ghi = gp + 1.f;
     float acc = 0.f;
-    for (int b = 0; b < nblk; ++b) {
-      const float4 h4 = reinterpret_cast<const float4*>(blk)[2 * b];
-      if (h4.y < glo || h4.x > ghi) continue;                  // (a NaN hull fails both tests and is summed directly)
-      if (h4.x >= glo && h4.y <= ghi) {
-        const float4 m4 = reinterpret_cast<const float4*>(blk)[2 * b + 1];
-        const float D = gp - h4.z;
-        acc += fmaf(fmaf(-D, D, 1.f), h4.w, fmaf(2.f * D, m4.x, -m4.y));
-      } else {
-        const int j1 = min(npairs, b * 32 + 32);
-        for (int j = b * 32; j < j1; ++j) {
+    for (int b0 = 0; b0 < nblk; b0 += 32) {
+      const int b = b0 + lane;
+      bool part = false;
+      if (b < nblk) {
+        const float4 h4 = blk4[2 * b];
+        const bool outside = (h4.y < glo) || (h4.x > ghi);
+        const bool inside = (h4.x >= glo) && (h4.y <= ghi);
+        if (inside) {
+          const float4 m4 = blk4[2 * b + 1];
+          const float D = gp - h4.z;
+          acc += fmaf(fmaf(-D, D, 1.f), h4.w, fmaf(2.f * D, m4.x, -m4.y));
+        }
+        part = !outside && !inside;                            // (a NaN hull fails both tests and is summed directly)
+      }
+      unsigned m = __ballot_sync(0xffffffffu, part);
+      while (m) {
+        const int j = (b0 + __ffs(m) - 1) * 32 + lane;
+        m &= m - 1;
+        if (j < npairs) {
           const float4 v = pairs[j];
           const float da = gp - v.x * sf, db = gp - v.y * sf;
           acc = fmaf(v.z, fmaxf(fmaf(-da, da, 1.f), 0.f), acc);
@@ -460,7 +473,9 @@ __device__ __noinline__ void fu_epan_blocks(const float4* __restrict__ pairs, in
         }
       }
     }
-    dens[g] = (double)acc * scale;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) dens[g] = (double)acc * scale;
   }
 }
 
@@ -961,8 +976,24 @@ numerator_marg_kernel(const NumArgs a) {
       __syncwarp();
       for (int g = lane; g < G; g += 32) dn[g] = epan_bins_sum(eb, eg_at(g), S0, S1, S2);
       __syncwarp();
-      for (int k = lane; k < Nz; k += 32) {
-        const double x = zgr[k];
+      // z-integral of the pixel: the four rows of an iteration (event grid, catalogue row, z-grid terms, completeness)
+      // are requested one iteration ahead -- they do not depend on the KDE, and 28 % of the kernel's warp samples
+      // sat on their L2 latency when each iteration loaded them right before use
+      auto rows_at = [&](int k, double& x, double& pc, float2& zv, double& pcm) {
+        x = zgr[k];
+        pc = has_cat ? pcat_ev[(size_t)p * Nz + k] : 0.0;
+        zv = zt ? __ldg(zt + k) : make_float2(0.f, 0.f);
+        pcm = has_cat ? pcompl_ev[k] : 0.0;
+      };
+      int k = lane;
+      double x = 0.0, pc = 0.0, pcm = 0.0;
+      float2 zv = make_float2(0.f, 0.f);
+      if (k < Nz) rows_at(k, x, pc, zv, pcm);
+      while (k < Nz) {
+        const int kn = k + 32;
+        double xn = 0.0, pcn = 0.0, pcmn = 0.0;
+        float2 zvn = make_float2(0.f, 0.f);
+        if (kn < Nz) rows_at(kn, xn, pcn, zvn, pcmn);
         double v = 0.0;
         if (x >= lb && x <= ub) {
           int i = (int)((x - lb) * inv_step);
@@ -974,17 +1005,16 @@ numerator_marg_kernel(const NumArgs a) {
           v = ((fabs(dx) <= 4.930380657631324e-32) ? f0 : f0 + ((x - x0) / dx) * (f1 - f0)) * scale;
         }
         if (pout) pout[(size_t)p * Nz + k] = v;
-        const double pc = has_cat ? pcat_ev[(size_t)p * Nz + k] : 0.0;
-        if (pc == -100.0) continue;
-        float2 zv;
-        if (zt) zv = __ldg(zt + k);
-        else {
-          const double zl = (k > 0) ? zgr[k - 1] : x, zr = (k < Nz - 1) ? zgr[k + 1] : x;
-          const F32Consts fc = make_f32_consts(a.mc, P, HC, tblk);
-          zv = zgrid_terms_f32(fc, make_cosmo_rate_f32(a.mc, P, HC), P, HC, a.mc.cosmo_model, x, 0.5 * (zr - zl));
+        if (pc != -100.0) {
+          if (!zt) {
+            const double zl = (k > 0) ? zgr[k - 1] : x, zr = (k < Nz - 1) ? zgr[k + 1] : x;
+            const F32Consts fc = make_f32_consts(a.mc, P, HC, tblk);
+            zv = zgrid_terms_f32(fc, make_cosmo_rate_f32(a.mc, P, HC), P, HC, a.mc.cosmo_model, x, 0.5 * (zr - zl));
+          }
+          const double pgal = has_cat ? fR * pc + (1.0 - pcm) * (double)zv.x : (double)zv.x;
+          like_acc += v * pgal * (double)zv.y;
         }
-        const double pgal = has_cat ? fR * pc + (1.0 - pcompl_ev[k]) * (double)zv.x : (double)zv.x;
-        like_acc += v * pgal * (double)zv.y;
+        k = kn; x = xn; pc = pcn; zv = zvn; pcm = pcmn;
       }
       __syncwarp();
     }

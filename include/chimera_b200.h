@@ -118,6 +118,8 @@ void chb_destroy(chb_handle* h);
  *   "kde_direct" 0 (default) | 1: one MUFU.EX2 per (grid point, sample) pair, no recurrence
  *   "bin_runs"   1 (default) | 0: non-fused binning by runs of sorted samples | one shared-memory atomic per sample
  *   "epan_blocks" 1 (default) | 0: fused kernel, unbinned Epanechnikov KDE by block moments of the sorted samples | direct pair sums
+ *   "zterms_gb"  16 (default): budget of the buffer of precomputed z-grid terms (n_hyper x Nev x Nz x 8 B); the one-launch
+ *                kernels take the hyper-points in batches beyond it (large walker batches)
  *   "stage_gb"   12 (default): budget of the stage buffer of the non-fused form; hyper-points are batched beyond it
  * Unknown names / out-of-range values: CHB_ERR_INVALID. */
 int chb_set_option(chb_handle* h, const char* name, double value);

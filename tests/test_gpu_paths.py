@@ -45,13 +45,15 @@ def _check(lle, ref, tol=2e-5):
   (4096, 300, {"kde_win_t2": 30}),                   # round 1's window threshold (default: 24 bits)
   (4096, 300, {"kde_win": 0}),                       # fused kernel, direct pair sums (no window plan)
   (4096, 48, {}),                                    # z grid too short for a window plan
-  (700, 300, {}),                                    # few samples: ragged last block, < 8 chunks -> direct sums
+  (700, 300, {}),                                    # few samples: ragged last block, 64-sample chunks
+  (300, 300, {}),                                    # too few samples for 8 chunks -> direct sums
   (4097, 300, {}),                                   # odd sample count: round-1 MODE-0 kernel, recurrence without windows
   (4096, 300, {"fused": 0}),                         # round-1 split kernels + windows
   (4096, 300, {"fused": 0, "split": 0}),             # round-1 MODE-0 kernel with the windowed KDE
   (4096, 300, {"fused": 0, "kde_win": 0}),           # split kernels, full-grid recurrence
   (4096, 300, {"fused": 0, "kde_direct": 1}),        # one MUFU.EX2 per pair
   (4096, 300, {"fused": 0, "stage_gb": 0.0003}),     # stage buffer for ONE hyper-point at a time: three batches
+  (4096, 300, {"zterms_gb": 0.00004}),               # z-grid terms for ONE hyper-point at a time: the fused kernel in three launches
 ])
 def test_fast_path_variants_match_oracle(cb, ns, nz, opt):
   th, zg, pop, sel, H0, ref = _case(cb, ns, nz)

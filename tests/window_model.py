@@ -27,8 +27,13 @@ def plan(G, n, h, iters=32, span=5, maxr=16):
   if R == 0:
     return None
   q = 4 * (32 // L)
-  chunk = max(iters * (32 // L), ((n + 31) // 32 + q - 1) // q * q)
-  nch = (n + chunk - 1) // chunk
+  it = iters
+  while True:                # few samples: shorter chunks rather than no windows (kde_win.cuh win_plan)
+    chunk = max(it * (32 // L), ((n + 31) // 32 + q - 1) // q * q)
+    nch = (n + chunk - 1) // chunk
+    if nch >= 8 or it <= 8:
+      break
+    it //= 2
   return (R, L, chunk, nch) if nch >= 8 else None
 
 
