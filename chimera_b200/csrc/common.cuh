@@ -91,6 +91,12 @@ bool numerator_fused_supported(const NumArgs& a);
 cudaError_t numerator_fused_configure(size_t smem);
 int numerator_fused_ctas_per_sm(size_t smem);
 cudaError_t launch_numerator_fused(const NumArgs& a, int grid, size_t smem, cudaStream_t s);
+// ... and its 128-thread instantiation (numerator_fused_nt128.cu)
+size_t numerator_fused_smem_bytes_nt128(const NumArgs& a);
+bool numerator_fused_supported_nt128(const NumArgs& a);
+cudaError_t numerator_fused_configure_nt128(size_t smem);
+int numerator_fused_ctas_per_sm_nt128(size_t smem);
+cudaError_t launch_numerator_fused_nt128(const NumArgs& a, int grid, size_t smem, cudaStream_t s);
 size_t numerator_marg_smem_bytes(const NumArgs& a);
 bool numerator_marg_supported(const NumArgs& a);
 cudaError_t numerator_marg_configure(size_t optin);

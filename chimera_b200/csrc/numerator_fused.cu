@@ -27,6 +27,24 @@
 #ifndef FU_NT
 #define FU_NT 256
 #endif
+// This file is compiled twice: as is (256 threads per CTA) and through numerator_fused_nt128.cu, which defines FU_NT = 128
+// and CHB_FU_VARIANT = _nt128 -- the second instantiation of the 1-D fused kernel for events with few samples (walker
+// batches with ~1000 samples per event), where the per-unit work every thread repeats (statistics, bandwidth, window plan)
+// and the barriers weigh as much as the sums: half the warps per unit, twice the units in flight.  The variant renames
+// the kernel and its five host entry points and leaves out the 'marginalized' kernel.
+#ifdef CHB_FU_VARIANT
+#define FU_CAT2(a, b) a##b
+#define FU_CAT(a, b) FU_CAT2(a, b)
+#define FU_NAME(x) FU_CAT(x, CHB_FU_VARIANT)
+#else
+#define FU_NAME(x) x
+#endif
+#define numerator_fused_kernel FU_NAME(numerator_fused_kernel)
+#define numerator_fused_smem_bytes FU_NAME(numerator_fused_smem_bytes)
+#define numerator_fused_supported FU_NAME(numerator_fused_supported)
+#define numerator_fused_configure FU_NAME(numerator_fused_configure)
+#define numerator_fused_ctas_per_sm FU_NAME(numerator_fused_ctas_per_sm)
+#define launch_numerator_fused FU_NAME(launch_numerator_fused)
 #define FU_NW (FU_NT / 32)
 #define FU_SUB 64                 // samples per warp iteration of the reweighting loop = granularity of the chunk summaries
 #define FU_INB (FU_SUB * 24)      // bytes of one block of packed samples: 64 x (float4 s4 + float2 l2)
@@ -54,7 +72,7 @@
 struct FusedPlan {                // byte offsets into dynamic shared memory
   int stage, rows, dens, bc, bs, bx, sub, summ, win, cr, red, total;
 };
-__host__ __device__ inline FusedPlan make_fused_plan(int Ns, int Nz, int B) {
+static __host__ __device__ inline FusedPlan make_fused_plan(int Ns, int Nz, int B) {
   FusedPlan p;
   const int G = Nz / 2;
   const int Bp = (B + 1) & ~1;
@@ -204,7 +222,7 @@ __device__ __forceinline__ void fu_cp_async_wait() { asm volatile("cp.async.wait
 // of blocks over the warps: bit-reproducible.  NOT inlined: the loop gets the kernel's whole register budget to itself
 // (the unit-level state of the caller is saved around the call once per unit instead of spilling inside the loop).
 template <int MASS>
-__device__ __noinline__ void fu_reweight(const double* __restrict__ f32blk, int rc, int rcs, int rms, int rm,
+static __device__ __noinline__ void fu_reweight(const double* __restrict__ f32blk, int rc, int rcs, int rms, int rm,
                                          const float* __restrict__ FC, const float4* __restrict__ s4,
                                          const float2* __restrict__ l2, int Ns, int want_lw_i, float4* __restrict__ stage,
                                          float4* __restrict__ sub, double* __restrict__ red, float4* __restrict__ inb) {
@@ -385,7 +403,7 @@ __device__ __forceinline__ void fu_direct_pass(const float4* __restrict__ pairs,
   }
 }
 // dens[g] = scale * sum over the data set; whole-CTA call; ends with dens[] written (no barrier after)
-__device__ __noinline__ void fu_direct(const float4* __restrict__ pairs, int npairs, int G, double gfirst, double hd,
+static __device__ __noinline__ void fu_direct(const float4* __restrict__ pairs, int npairs, int G, double gfirst, double hd,
                                           float sf, float koff, bool gauss, double scale, double* __restrict__ rows,
                                           double* __restrict__ dens) {
   if (G <= 160) {
@@ -416,7 +434,7 @@ __device__ __noinline__ void fu_direct(const float4* __restrict__ pairs, int npa
 // result does not depend on the samples actually being sorted -- only the cost does.
 // blk: 8 floats per block {lo, hi, c, M0, M1, M2, -, -} (the per-warp rows are idle in this path).  Whole-CTA call; ends
 // with dens[] written (no barrier after).
-__device__ __noinline__ void fu_epan_blocks(const float4* __restrict__ pairs, int npairs, int G, double gfirst, double hd,
+static __device__ __noinline__ void fu_epan_blocks(const float4* __restrict__ pairs, int npairs, int G, double gfirst, double hd,
                                             float sf, double scale, float* __restrict__ blk, double* __restrict__ dens) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nblk = (npairs + 31) / 32;
@@ -536,7 +554,7 @@ __device__ __forceinline__ double epan_bins_sum(const EpanBins& eb, double g, co
 
 // Windowed recurrence KDE of the staged samples (kde_win.cuh) -- NOT inlined, for the same reason as fu_reweight.
 // Merges the 64-sample block summaries into the plan's chunks (scaled units, weights normalised), then phases B and C.
-__device__ __noinline__ void fu_kde_win(const float4* __restrict__ stage, int Ns, int G, double gfirst, double hd, int R,
+static __device__ __noinline__ void fu_kde_win(const float4* __restrict__ stage, int Ns, int G, double gfirst, double hd, int R,
                                         int LPS, int chunk, int nchunks, double scale, float sf, float koff, float t2,
                                         const float4* __restrict__ sub, float4* __restrict__ summ, int2* __restrict__ win,
                                         float* __restrict__ cr, double* __restrict__ rows, double* __restrict__ dens) {
@@ -597,9 +615,11 @@ numerator_fused_kernel(const NumArgs a) {
     //  and two grid points per thread-round in the z-integral removed two barriers per unit but cost registers: C3 +-0,
     //  C1 and the binned path 3-4 % slower -- not adopted)
     __syncthreads();                                         // the previous unit is done with every shared array
-    if (tid < CHB_NPAR) P[tid] = a.hyper[(size_t)h * CHB_NPAR + tid];
-    else if (tid >= 64 && tid < 64 + CHB_NHC) HC[tid - 64] = a.HC[(size_t)h * CHB_NHC + tid - 64];
-    else if (tid >= 128 && tid < 128 + CHB_NFC) FC[tid - 128] = __ldg(reinterpret_cast<const float*>(tblk + lay.f32_fc()) + tid - 128);
+    for (int i = tid; i < CHB_NPAR + CHB_NHC + CHB_NFC; i += FU_NT) {      // (any thread count: 128 or 256)
+      if (i < CHB_NPAR) P[i] = a.hyper[(size_t)h * CHB_NPAR + i];
+      else if (i < CHB_NPAR + CHB_NHC) HC[i - CHB_NPAR] = a.HC[(size_t)h * CHB_NHC + i - CHB_NPAR];
+      else FC[i - CHB_NPAR - CHB_NHC] = __ldg(reinterpret_cast<const float*>(tblk + lay.f32_fc()) + i - CHB_NPAR - CHB_NHC);
+    }
     __syncthreads();
 
     // ---- stage 1: reweighting ---------------------------------------------------------------
@@ -832,6 +852,7 @@ numerator_fused_kernel(const NumArgs a) {
   }
 }
 
+#ifndef CHB_FU_VARIANT
 // ==================================================================================================================
 // 'marginalized' kind with binning (the reference's default options, examples/test1dgalaxies.ipynb): one fused kernel,
 // warp per pixel.  likelihood.py:160-205: per pixel the in-pixel samples are binned on [min z (all samples), max z (pixel)]
@@ -1048,6 +1069,8 @@ cudaError_t launch_numerator_marg(const NumArgs& a, int grid, size_t smem, cudaS
   numerator_marg_kernel<<<grid, FU_NT, smem, s>>>(a);
   return cudaGetLastError();
 }
+
+#endif  // CHB_FU_VARIANT
 
 cudaError_t numerator_fused_configure(size_t optin) {      // see numerator_f32_configure
   cudaFuncAttributes fa;
