@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("CHB_BUILD_OUT") or os.path.join(HERE, "libchimera_b200.so")
-SOURCES = ["tables.cu", "selection.cu", "numerator.cu", "numerator_f32.cu", "numerator_fused.cu", "numerator_fused_nt128.cu", "api.cu", "microbench.cu", "setup.cu"]
+SOURCES = ["tables.cu", "selection.cu", "numerator.cu", "numerator_f32.cu", "numerator_fused.cu", "numerator_fused_nt128.cu", "numerator_fused_nt64.cu", "api.cu", "microbench.cu", "setup.cu"]
 # setup.cu holds the HEALPix index arithmetic: no FMA contraction, so that it rounds like the host libraries
 EXTRA_FLAGS = {"setup.cu": ["-fmad=false"]}
 HEADERS = ["numerator_fused.cu", "models.cuh", "models_f32.cuh", "kde_f32.cuh", "kde_win.cuh", "common.cuh", "devguard.cuh", "stage.cuh", os.path.join("..", "..", "include", "chimera_b200.h")]

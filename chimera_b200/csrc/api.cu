@@ -77,7 +77,7 @@ struct chb_handle {
   int opt_kde_direct = 0;                  // 1: one MUFU.EX2 per pair (no recurrence)
   int opt_bin_runs = 1;                    // round-1 path: binning by runs of the sorted samples
   int opt_epan_blocks = 1;                 // fused kernel, unbinned Epanechnikov: block moments (0: direct pair sums)
-  int opt_fused_nt = 0;                    // threads per CTA of the fused 1-D kernel: 0 = 128 for Ns <= 2048 else 256
+  int opt_fused_nt = 0;                    // threads per CTA of the fused 1-D kernel: 0 = 64 for Ns <= 1024, 128 for Ns <= 2048, else 256
   double opt_zterms_gb = 16.0;             // budget of the z-grid-term buffer; the one-launch kernels batch the hyper-points beyond it
   double opt_stage_gb = 12.0;              // round-1 path: budget of the {z, w} stage buffer
   DevBuf<double> catA, catB;
@@ -429,11 +429,15 @@ static int eval_impl(chb_handle* h, int64_t n_hyper, const double* d_hyper, doub
       // (1) 1-D kinds: ONE fused kernel per step (numerator_fused.cu), samples never leave shared memory.
       // Events with few samples run the 128-thread instantiation (six CTAs per SM): the per-unit work every thread
       // repeats and the barriers weigh as much as the sums there (option fused_nt: 0 = by sample count, 128, 256).
-      const bool nt128 = h->opt_fused_nt == 128 || (h->opt_fused_nt == 0 && h->Ns <= 2048);
-      const size_t ff = nt128 ? numerator_fused_smem_bytes_nt128(a) : numerator_fused_smem_bytes(a);
+      // (measured on C5, 1000 samples per event: 256 threads 1.92 s, 128 threads 1.51 s, 64 threads 1.43 s per step of
+      //  4.1e7 units; on C3, 5000 samples: 256 threads 21.7 ms, 128 threads 22.2 ms)
+      const bool nt64 = h->opt_fused_nt == 64 || (h->opt_fused_nt == 0 && h->Ns <= 1024);
+      const bool nt128 = !nt64 && (h->opt_fused_nt == 128 || (h->opt_fused_nt == 0 && h->Ns <= 2048));
+      const size_t ff = nt64 ? numerator_fused_smem_bytes_nt64(a) : nt128 ? numerator_fused_smem_bytes_nt128(a) : numerator_fused_smem_bytes(a);
       bool fused = h->opt_fused && numerator_fused_supported(a) && ff <= fit;
       if (fused && h->fused_per < 0) {
-        if (nt128) h->fused_per = (numerator_fused_configure_nt128(optin) == cudaSuccess) ? numerator_fused_ctas_per_sm_nt128(ff) : 0;
+        if (nt64) h->fused_per = (numerator_fused_configure_nt64(optin) == cudaSuccess) ? numerator_fused_ctas_per_sm_nt64(ff) : 0;
+        else if (nt128) h->fused_per = (numerator_fused_configure_nt128(optin) == cudaSuccess) ? numerator_fused_ctas_per_sm_nt128(ff) : 0;
         else h->fused_per = (numerator_fused_configure(optin) == cudaSuccess) ? numerator_fused_ctas_per_sm(ff) : 0;
         cudaGetLastError();
       }
@@ -528,7 +532,8 @@ static int eval_impl(chb_handle* h, int64_t n_hyper, const double* d_hyper, doub
             const long long ub = (long long)h->Nev * nh;
             const int grid = (int)std::min<long long>(ub, (long long)h->sm_count * per);
             h->num_grid = grid;
-            if (fused && nt128) { CU(launch_numerator_fused_nt128(b, grid, smem, s), "numerator_fused launch"); }
+            if (fused && nt64) { CU(launch_numerator_fused_nt64(b, grid, smem, s), "numerator_fused launch"); }
+            else if (fused && nt128) { CU(launch_numerator_fused_nt128(b, grid, smem, s), "numerator_fused launch"); }
             else if (fused) { CU(launch_numerator_fused(b, grid, smem, s), "numerator_fused launch"); }
             else { CU(launch_numerator_marg(b, grid, smem, s), "numerator_marg launch"); }
             if (!first) h->launches++;             // the common `launches++` below counts the first one
@@ -638,7 +643,7 @@ int chb_set_option(chb_handle* h, const char* name, double value) {
   else if (n == "kde_direct") h->opt_kde_direct = value != 0.0;
   else if (n == "bin_runs") h->opt_bin_runs = value != 0.0;
   else if (n == "epan_blocks") h->opt_epan_blocks = value != 0.0;
-  else if (n == "fused_nt") { if (value != 0.0 && value != 128.0 && value != 256.0) return fail(h, CHB_ERR_INVALID, "fused_nt must be 0, 128 or 256"); h->opt_fused_nt = (int)value; }
+  else if (n == "fused_nt") { if (value != 0.0 && value != 64.0 && value != 128.0 && value != 256.0) return fail(h, CHB_ERR_INVALID, "fused_nt must be 0, 64, 128 or 256"); h->opt_fused_nt = (int)value; }
   else if (n == "zterms_gb") { if (!(value > 0.0)) return fail(h, CHB_ERR_INVALID, "zterms_gb must be positive"); h->opt_zterms_gb = value; }
   else if (n == "stage_gb") { if (!(value > 0.0)) return fail(h, CHB_ERR_INVALID, "stage_gb must be positive"); h->opt_stage_gb = value; }
   else return fail(h, CHB_ERR_INVALID, "unknown option '" + n + "'");

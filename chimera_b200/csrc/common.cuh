@@ -97,6 +97,11 @@ bool numerator_fused_supported_nt128(const NumArgs& a);
 cudaError_t numerator_fused_configure_nt128(size_t smem);
 int numerator_fused_ctas_per_sm_nt128(size_t smem);
 cudaError_t launch_numerator_fused_nt128(const NumArgs& a, int grid, size_t smem, cudaStream_t s);
+size_t numerator_fused_smem_bytes_nt64(const NumArgs& a);
+bool numerator_fused_supported_nt64(const NumArgs& a);
+cudaError_t numerator_fused_configure_nt64(size_t smem);
+int numerator_fused_ctas_per_sm_nt64(size_t smem);
+cudaError_t launch_numerator_fused_nt64(const NumArgs& a, int grid, size_t smem, cudaStream_t s);
 size_t numerator_marg_smem_bytes(const NumArgs& a);
 bool numerator_marg_supported(const NumArgs& a);
 cudaError_t numerator_marg_configure(size_t optin);

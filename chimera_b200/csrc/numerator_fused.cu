@@ -27,11 +27,11 @@
 #ifndef FU_NT
 #define FU_NT 256
 #endif
-// This file is compiled twice: as is (256 threads per CTA) and through numerator_fused_nt128.cu, which defines FU_NT = 128
-// and CHB_FU_VARIANT = _nt128 -- the second instantiation of the 1-D fused kernel for events with few samples (walker
+// This file is compiled three times: as is (256 threads per CTA) and through numerator_fused_nt128.cu / _nt64.cu, which
+// define FU_NT and CHB_FU_VARIANT -- further instantiations of the 1-D fused kernel for events with few samples (walker
 // batches with ~1000 samples per event), where the per-unit work every thread repeats (statistics, bandwidth, window plan)
-// and the barriers weigh as much as the sums: half the warps per unit, twice the units in flight.  The variant renames
-// the kernel and its five host entry points and leaves out the 'marginalized' kernel.
+// and the barriers weigh as much as the sums: fewer warps per unit, more units in flight.  A variant renames the
+// kernel and its five host entry points and leaves out the 'marginalized' kernel.
 #ifdef CHB_FU_VARIANT
 #define FU_CAT2(a, b) a##b
 #define FU_CAT(a, b) FU_CAT2(a, b)

@@ -118,8 +118,8 @@ void chb_destroy(chb_handle* h);
  *   "kde_direct" 0 (default) | 1: one MUFU.EX2 per (grid point, sample) pair, no recurrence
  *   "bin_runs"   1 (default) | 0: non-fused binning by runs of sorted samples | one shared-memory atomic per sample
  *   "epan_blocks" 1 (default) | 0: fused kernel, unbinned Epanechnikov KDE by block moments of the sorted samples | direct pair sums
- *   "fused_nt"   0 (default) | 128 | 256: threads per CTA of the fused 1-D kernel; 0 picks 128 (six CTAs per SM) for events with
- *                <= 2048 samples, where per-unit overheads dominate, else 256
+ *   "fused_nt"   0 (default) | 64 | 128 | 256: threads per CTA of the fused 1-D kernel; 0 picks 64 (twelve CTAs per SM) for events
+ *                with <= 1024 samples and 128 (six) up to 2048, where the per-unit overheads dominate, else 256 (three)
  *   "zterms_gb"  16 (default): budget of the buffer of precomputed z-grid terms (n_hyper x Nev x Nz x 8 B); the one-launch
  *                kernels take the hyper-points in batches beyond it (large walker batches)
  *   "stage_gb"   12 (default): budget of the stage buffer of the non-fused form; hyper-points are batched beyond it

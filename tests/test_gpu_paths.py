@@ -49,6 +49,7 @@ def _check(lle, ref, tol=2e-5):
   (300, 300, {}),                                    # too few samples for 8 chunks -> direct sums
   (4096, 300, {"fused_nt": 128}),                    # the 128-thread instantiation (default for Ns <= 2048) on a long event
   (700, 300, {"fused_nt": 256}),                     # ... and the 256-thread one on a short event
+  (700, 300, {"fused_nt": 64}),                      # 64-thread instantiation
   (4097, 300, {}),                                   # odd sample count: round-1 MODE-0 kernel, recurrence without windows
   (4096, 300, {"fused": 0}),                         # round-1 split kernels + windows
   (4096, 300, {"fused": 0, "split": 0}),             # round-1 MODE-0 kernel with the windowed KDE
