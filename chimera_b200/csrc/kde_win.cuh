@@ -242,8 +242,10 @@ __device__ __forceinline__ void kde_win_BC(const float2* __restrict__ xw, int n,
   // ---- phase B: lane c holds chunk c; every warp walks its share of the grid points: M(g) is one warp-wide max,
   // the need test one compare per lane, the hull of the needed points accumulates in registers ------------
   const float lgchunk = lg2f_((float)pl.chunk);
-  const float4 my = (lane < pl.nchunks) ? summ[lane] : make_float4(INFINITY, -INFINITY, -INFINITY, 0.f);
+  // (measured: packing two grid points per step into the half-warps for events with <= 16 chunks, with a half-warp
+  //  redux.sync, made C5 11 % SLOWER -- the partial-mask redux is not the one-instruction path)
   {
+    const float4 my = (lane < pl.nchunks) ? summ[lane] : make_float4(INFINITY, -INFINITY, -INFINITY, 0.f);
     const float myU = my.z + lgchunk, gf = (float)gfirst;
     int gmin = G, gmax = -1;
     for (int g = warp; g < G; g += NW) {

@@ -608,6 +608,7 @@ numerator_fused_kernel(const NumArgs a) {
   const bool want_lw = gauss && !a.binning;                  // the stage carries log2 w for the Gaussian pair sums
 
   const long long units = (long long)a.Nev * a.n_hyper;
+  const double inv_ns = 1.0 / (double)Ns;
   for (long long unit = blockIdx.x; unit < units; unit += gridDim.x) {
     const int ev = (int)(unit / a.n_hyper), h = (int)(unit % a.n_hyper);
     const double* tblk = a.tabs + (size_t)h * lay.total() + lay.off_f32();
@@ -664,9 +665,11 @@ numerator_fused_kernel(const NumArgs a) {
     const float z0 = (float)red[95];
     const double s1 = st.a, s2 = st.b;
     const double zmn = (double)z0 + (double)st.mn, zmx = (double)z0 + (double)st.mx;
-    const double dzmean = st.c / Ns;
-    const double zstd = sqrt(fmax(st.d / Ns - dzmean * dzmean, 0.0));    // one-pass variance about z0
-    const double norm = s1 / Ns;                  // likelihood.py:111
+    // (fp64 divisions are ~25 instructions each and every thread repeats this section: 1/Ns is taken once per kernel,
+    //  1/bw once per unit, the effective sample size of kde1d re-uses the one of the N_eff gate)
+    const double dzmean = st.c * inv_ns;
+    const double zstd = sqrt(fmax(st.d * inv_ns - dzmean * dzmean, 0.0));    // one-pass variance about z0
+    const double norm = s1 * inv_ns;              // likelihood.py:111
     const double neff = s1 * s1 / s2;             // likelihood.py:112
     const bool ok = (neff >= a.pe_neff);
 
@@ -687,15 +690,16 @@ numerator_fused_kernel(const NumArgs a) {
 
     if (!a.binning) {
       // ---- bandwidth (utils/math.py:62-70), every thread the same value ----------------------------
-      const double neff_k = 1.0 / (s2 / (s1 * s1));
+      const double neff_k = neff;                  // 1 / sum((w/W)^2) (utils/math.py:62) = W^2 / sum(w^2)
       double bw;
       if (a.bw_method == CHB_BW_SCOTT) bw = (double)ex2f_(-0.2f * lg2f_((float)neff_k)) * zstd;
-      else if (a.bw_method == CHB_BW_SILVERMAN) bw = (double)ex2f_(-0.2f * lg2f_((float)(neff_k * 3.0 / 4.0))) * zstd;
+      else if (a.bw_method == CHB_BW_SILVERMAN) bw = (double)ex2f_(-0.2f * lg2f_((float)(neff_k * 0.75))) * zstd;
       else bw = a.bw_value * zstd;
-      const double s = gauss ? 0.8493218002880191 / bw : 1.0 / bw;       // sqrt(log2(e)/2) / bw
+      const double inv_bw = 1.0 / bw;
+      const double s = (gauss ? 0.8493218002880191 : 1.0) * inv_bw;      // sqrt(log2(e)/2) / bw
       const float sf = (float)s;
       const double gfirst = (lb - (double)z0) * (double)sf, hd = step * (double)sf;
-      const double scale = norm * (gauss ? 0.3989422804014327 : 0.75) / bw;
+      const double scale = norm * (gauss ? 0.3989422804014327 : 0.75) * inv_bw;
       WinPlan wp;
       const bool windowed = gauss && a.kde_win_iters > 0 && Nz >= 64 &&
                             win_plan(G, Ns, (float)hd, a.kde_win_iters, 32, wp, FU_SUB, a.win_t2);

@@ -87,26 +87,47 @@ build_tables_kernel(ModelCfg mc, int n_hyper, const double* __restrict__ hyper, 
   }
   __syncthreads();
 
-  if (tid == 0) {            // cumtrapz(1/E, z)  (utils/math.py:22-26)
-    double prev = ys[0], acc = 0.0;
-    ys[0] = 0.0;
-    for (int i = 1; i < rc; ++i) {
-      double cur = ys[i];
-      acc += 0.5 * (prev + cur) * (zs[i] - zs[i - 1]);
-      ys[i] = acc;
-      prev = cur;
+  // cumtrapz(1/E, z) (utils/math.py:22-26) by warp 0, cumtrapz(p2) and trapz(p1) by warp 1: every lane sums the
+  // trapezoid increments of a contiguous segment left to right, the segment totals are scanned with shuffles and each
+  // lane then writes its running sums starting from its offset.  (One thread walking the ~1000-knot tables alone was
+  // 80 us per step, the largest per-step cost that does not shrink when the events are sharded over GPUs; the
+  // association differs from a strictly sequential cumsum by a few ulp.)
+  {
+    const int lane = tid & 31, warp = tid >> 5;
+    if (warp < 2) {
+      double* y = (warp == 0) ? ys : p2;
+      const double* x = (warp == 0) ? zs : ms;
+      const int n = (warp == 0) ? rc : rm;
+      const int seg = (n - 1 + 31) / 32;
+      const int a0 = min(n, 1 + lane * seg), a1 = min(n, a0 + seg);
+      const double first_prev = (a0 < n) ? y[a0 - 1] : 0.0;      // the ORIGINAL value left of the segment
+      double tot = 0.0, nrm = 0.0, prev = first_prev;
+      for (int i = a0; i < a1; ++i) {
+        const double cur = y[i], dx = x[i] - x[i - 1];
+        tot += 0.5 * (prev + cur) * dx;
+        if (warp == 1) nrm += dx * (p1[i] + p1[i - 1]) / 2.0;
+        prev = cur;
+      }
+      double off = tot;                                        // inclusive scan of the segment totals -> exclusive offset
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const double v = __shfl_up_sync(0xffffffffu, off, o); if (lane >= o) off += v; }
+      off -= tot;
+      if (warp == 1) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
+        if (lane == 0) HC[HC_NORM_P_M1] = nrm;
+      }
+      __syncwarp();                                            // every lane has read its originals
+      double acc = off;
+      prev = first_prev;
+      for (int i = a0; i < a1; ++i) {
+        const double cur = y[i];
+        acc += 0.5 * (prev + cur) * (x[i] - x[i - 1]);
+        y[i] = acc;
+        prev = cur;
+      }
+      if (lane == 0) y[0] = 0.0;
     }
-  } else if (tid == 32) {    // cumtrapz(p2) and trapz(p1)
-    double prev = p2[0], acc = 0.0, nrm = 0.0;
-    p2[0] = 0.0;
-    for (int i = 1; i < rm; ++i) {
-      double cur = p2[i], dx = ms[i] - ms[i - 1];
-      acc += 0.5 * (prev + cur) * dx;
-      p2[i] = acc;
-      prev = cur;
-      nrm += dx * (p1[i] + p1[i - 1]) / 2.0;
-    }
-    HC[HC_NORM_P_M1] = nrm;
   }
   __syncthreads();
 
