@@ -541,6 +541,38 @@ __device__ __forceinline__ void epan_bins_prefix(const EpanBins& eb, const float
     S0[i + 1] = e0; S1[i + 1] = e1; S2[i + 1] = e2;
   }
 }
+// the same prefix tables by the WHOLE CTA (the 1-D fused kernel): every thread takes a segment of ceil(B / threads) bins,
+// warp scans + the warp totals through `wtot` (3 * FU_NW doubles) -- one warp alone spent ~600 dependent fp64
+// instructions here with the other seven waiting on the barrier behind it (6 % of the reference-default configuration).
+// Contains one __syncthreads(); the caller's barrier publishes the tables.
+__device__ __forceinline__ void epan_bins_prefix_cta(const EpanBins& eb, const float* __restrict__ bins, double invW,
+                                                     double* __restrict__ S0, double* __restrict__ S1, double* __restrict__ S2,
+                                                     double* __restrict__ wtot) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int seg = (eb.B + FU_NT - 1) / FU_NT, b0 = min(eb.B, tid * seg), b1 = min(eb.B, b0 + seg);
+  double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+  for (int i = b0; i < b1; ++i) {
+    const double wn = (double)bins[i] * invW, u = (epan_bin_centre(eb, i) - eb.cmid) * eb.inv_bw;
+    t0 += wn; t1 += wn * u; t2 += wn * u * u;
+  }
+  double e0 = t0, e1 = t1, e2 = t2;                           // inclusive scan over the warp's threads
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double y0 = __shfl_up_sync(0xffffffffu, e0, o), y1 = __shfl_up_sync(0xffffffffu, e1, o), y2 = __shfl_up_sync(0xffffffffu, e2, o);
+    if (lane >= o) { e0 += y0; e1 += y1; e2 += y2; }
+  }
+  if (lane == 31) { wtot[warp * 3] = e0; wtot[warp * 3 + 1] = e1; wtot[warp * 3 + 2] = e2; }
+  __syncthreads();
+  double o0 = 0.0, o1 = 0.0, o2 = 0.0;
+  for (int w = 0; w < warp; ++w) { o0 += wtot[w * 3]; o1 += wtot[w * 3 + 1]; o2 += wtot[w * 3 + 2]; }
+  e0 += o0 - t0; e1 += o1 - t1; e2 += o2 - t2;                // exclusive prefix of this thread's segment
+  if (tid == 0) { S0[0] = 0.0; S1[0] = 0.0; S2[0] = 0.0; }
+  for (int i = b0; i < b1; ++i) {
+    const double wn = (double)bins[i] * invW, u = (epan_bin_centre(eb, i) - eb.cmid) * eb.inv_bw;
+    e0 += wn; e1 += wn * u; e2 += wn * u * u;
+    S0[i + 1] = e0; S1[i + 1] = e1; S2[i + 1] = e2;
+  }
+}
 // sum_b w'_b (1 - ((g - c_b)/bw)^2) over the bins with |g - c_b| <= bw (bins exactly on the edge contribute 0 either way)
 __device__ __forceinline__ double epan_bins_sum(const EpanBins& eb, double g, const double* __restrict__ S0,
                                                 const double* __restrict__ S1, const double* __restrict__ S2) {
@@ -762,7 +794,7 @@ numerator_fused_kernel(const NumArgs a) {
         // Epanechnikov (the reference's default kernel): prefix sums over the bins, O(1) per grid point
         const EpanBins eb = make_epan_bins(zmn, zmx, B, bw);
         double* S0 = bc; double* S1 = bc + (B + 2); double* S2 = bc + 2 * (B + 2);
-        if (warp == 0) epan_bins_prefix(eb, binsf, 1.0 / W, S0, S1, S2);
+        epan_bins_prefix_cta(eb, binsf, 1.0 / W, S0, S1, S2, red + 6 * FU_NW);      // (red[0 .. 6 FU_NW) may still be read: fu_block_stats)
         __syncthreads();
         const double scale = norm * 0.75 / bw;
         for (int g = tid; g < G; g += FU_NT) dens[g] = epan_bins_sum(eb, eg_at(g), S0, S1, S2) * scale;
