@@ -289,7 +289,8 @@ static int prepare(chb_handle* h) {
   // 1-D kinds (both arithmetic modes): every per-event reduction is order-independent, so the samples of every event
   // are sorted by dL.  z_from_dGW is monotone in dL, hence the reweighted z's come out sorted for every hyper-point and
   // the windowed KDEs (kde_win.cuh, kde_win64.cuh) only visit the grid points near each chunk of samples.
-  h->sorted = (kind == CHB_PGW_1D || kind == CHB_PGW_APPROX);
+  // ('full': the 3-D KDE skips blocks of dL-sorted samples that are far from a tile of evaluation points in z)
+  h->sorted = (kind == CHB_PGW_1D || kind == CHB_PGW_APPROX || kind == CHB_PGW_FULL);
   const bool bucket = !h->sorted && h->have_pixels && !h->h_pe_pix.empty();
   const bool sky = !h->h_ra.empty();
   std::vector<double> t1, t2, t3, t4, t5, t6;

@@ -676,20 +676,31 @@ numerator_f32_kernel(const NumArgs a) {
         const double f2 = factor * factor;
         const double i00 = a00 / det / f2, i01 = a01 / det / f2, i02 = a02 / det / f2;
         const double i11 = a11 / det / f2, i12 = a12 / det / f2, i22 = a22 / det / f2;
-        const double l00 = sqrt(i00), l10 = i01 / l00, l20 = i02 / l00;
-        const double l11 = sqrt(i11 - l10 * l10), l21 = (i12 - l20 * l10) / l11;
-        const double l22 = sqrt(i22 - l20 * l20 - l21 * l21);
+        // Cholesky factor of the inverse covariance with the variables ordered (dec, ra, z): the quadratic form is the
+        // same for any order, and with z last the third whitened coordinate y2 = l22 (z - mean z) depends on z alone --
+        // monotone in z, so the dL-sorted samples are sorted in y2 and whole blocks of them can be skipped for
+        // evaluation points that are far away in z (below)
+        const double j00 = i22, j01 = i12, j02 = i02, j11 = i11, j12 = i01, j22 = i00;
+        const double l00 = sqrt(j00), l10 = j01 / l00, l20 = j02 / l00;
+        const double l11 = sqrt(j11 - l10 * l10), l21 = (j12 - l20 * l10) / l11;
+        const double l22 = sqrt(j22 - l20 * l20 - l21 * l21);
         L[0] = l00; L[1] = l10; L[2] = l11; L[3] = l20; L[4] = l21; L[5] = l22;
         L[6] = log(l00) + log(l11) + log(l22) - 1.5 * log(2.0 * CHB_PI);
       }
       __syncthreads();
       const double l00 = L[0], l10 = L[1], l11 = L[2], l20 = L[3], l21 = L[4], l22 = L[5], lognorm = L[6];
       const double ps = 0.8493218002880191;            // sqrt(log2(e)/2)
+      // whitened coordinates of (z, ra, dec) deviations r0, r1, r2
+      auto whiten = [&](double r0, double r1, double r2, float& y0, float& y1, float& y2) {
+        y0 = (float)((r2 * l00 + r1 * l10 + r0 * l20) * ps);
+        y1 = (float)((r1 * l11 + r0 * l21) * ps);
+        y2 = (float)((r0 * l22) * ps);
+      };
       for (int j = tid; j < Ns; j += NT) {
         const float2 v = zw[j];
-        const double r0 = (double)v.x - m0, r1 = ra[j] - m1, r2 = dec[j] - m2;
-        yw[j] = make_float4((float)((r0 * l00 + r1 * l10 + r2 * l20) * ps), (float)((r1 * l11 + r2 * l21) * ps),
-                            (float)((r2 * l22) * ps), (float)((double)v.y / W));
+        float y0, y1, y2;
+        whiten((double)v.x - m0, ra[j] - m1, dec[j] - m2, y0, y1, y2);
+        yw[j] = make_float4(y0, y1, y2, (float)((double)v.y / W));
       }
       if (pout) for (int i = tid; i < Pp * Nz; i += NT) pout[i] = 0.0;
       const double zlo = zmn - a.cut_grid * zstd, zhi = zmx + a.cut_grid * zstd;   // likelihood.py:225
@@ -706,32 +717,87 @@ numerator_f32_kernel(const NumArgs a) {
       const int npts = npix * nmask;
       constexpr int FR = 4;                       // evaluation points per lane: two packed pairs (FADD2 / FMUL2 / FFMA2)
       const double enorm = exp(lognorm) * norm;
+      // ---- hulls of the 64-sample blocks in y2 and their heaviest weight (one warp per block) ---------------------
+      constexpr int SB = 64;
+      const int nblk = (Ns + SB - 1) / SB;
+      float4* blkh = reinterpret_cast<float4*>(part);          // {min y2, max y2, log2 max w, -}; `part` is idle for this kind
+      const bool windows = nblk * 16 <= ((NW * Nz + 1) / 2) * 8 && a.kde_win_iters > 0;
+      if (windows) {
+        for (int b = warp; b < nblk; b += NW) {
+          float lo = INFINITY, hi = -INFINITY, wm = 0.f;
+          for (int jj = b * SB + lane; jj < min(Ns, b * SB + SB); jj += 32) {
+            const float4 v = yw[jj];
+            lo = fminf(lo, v.z); hi = fmaxf(hi, v.z); wm = fmaxf(wm, v.w);
+          }
+          lo = warp_min_f32(lo); hi = warp_max_f32(hi); wm = warp_max_f32(wm);
+          if (lane == 0) blkh[b] = make_float4(lo, hi, (wm > 0.f) ? lg2f_(wm) : -INFINITY, 0.f);
+        }
+        __syncthreads();
+      }
+      // Evaluation points ordered pixel-fastest: a tile of 32 FR consecutive points spans only a few z values, i.e. a
+      // narrow range of y2.
       const int ntiles = (npts + 32 * FR - 1) / (32 * FR);
-      // Work items = (tile of 32 FR points) x (slice of the samples): the likelihood is linear in the pair sums, so a
-      // warp multiplies its PARTIAL sum of a point by the point's catalogue factor; slices make the item count a
-      // multiple of the warp count (34 tiles on 8 warps left 1/7 of the warps idle at the end).  p_gw output wants
-      // complete sums per point: one slice then.
-      int S = 1;
-      while (!pout && (ntiles * S) % NW != 0 && S < 8 && Ns / (2 * S) >= 256) S *= 2;
-      const int per = (((Ns + S - 1) / S) + 3) & ~3;
-      for (int it = warp; it < ntiles * S; it += NW) {
-        const int t = it / S, jlo = (it - t * S) * per, jhi = min(Ns, jlo + per);
-        float q0[FR], q1[FR], q2[FR], acc[FR];
-        int pk[FR];
+      auto tile_points = [&](int t, float (&q0)[FR], float (&q1)[FR], float (&q2)[FR], int (&pk)[FR], float& t2lo, float& t2hi) {
+        t2lo = INFINITY; t2hi = -INFINITY;
 #pragma unroll
         for (int r = 0; r < FR; ++r) {
           const int i = t * 32 * FR + r * 32 + lane;
-          pk[r] = -1; acc[r] = 0.f;
+          pk[r] = -1;
           q0[r] = q1[r] = q2[r] = 1.0e18f;
           if (i < npts) {
-            const int p = i / nmask, k = kmask[i - p * nmask];
+            const int kk = i / npix, p = i - kk * npix, k = kmask[kk];
             pk[r] = p * Nz + k;
-            const double r0 = zgrid[k] - m0, r1 = rap[p] - m1, r2 = dep[p] - m2;
-            q0[r] = (float)((r0 * l00 + r1 * l10 + r2 * l20) * ps);
-            q1[r] = (float)((r1 * l11 + r2 * l21) * ps);
-            q2[r] = (float)((r2 * l22) * ps);
+            whiten(zgrid[k] - m0, rap[p] - m1, dep[p] - m2, q0[r], q1[r], q2[r]);
+            t2lo = fminf(t2lo, q2[r]); t2hi = fmaxf(t2hi, q2[r]);
           }
         }
+        t2lo = warp_min_f32(t2lo); t2hi = warp_max_f32(t2hi);
+      };
+      // Window of a tile: a LOWER bound of the largest single term at each of its points from every 32nd sample (M,
+      // minimum over the points), against the UPPER bound of a whole block, 64 x its heaviest weight at the block's
+      // nearest approach in y2 alone.  A block is skipped when that bound is below 2^-t2 of M (t2 = 24 bits): what is dropped
+      // is below 2^-24 of the largest term AT EVERY POINT of the tile, so far tails keep their relative accuracy.  (M = -inf,
+      // every block visited, when a point sees only underflowing terms.)  One pass over the tiles fills Mt[].
+      float* Mt = reinterpret_cast<float*>(eg);                // `eg` is idle for this kind
+      const bool win3 = windows && ntiles <= 2 * Nz;
+      if (win3) {
+        for (int t = warp; t < ntiles; t += NW) {
+          float q0[FR], q1[FR], q2[FR], mp[FR], t2lo, t2hi;
+          int pk[FR];
+          tile_points(t, q0, q1, q2, pk, t2lo, t2hi);
+#pragma unroll
+          for (int r = 0; r < FR; ++r) mp[r] = -INFINITY;
+          for (int jj = 0; jj < Ns; jj += 32) {
+            const float4 v = yw[jj];
+            const float lw = lg2f_(v.w);                         // (w = 0 -> -inf: never the maximum)
+#pragma unroll
+            for (int r = 0; r < FR; ++r) {
+              const float d0 = v.x - q0[r], d1 = v.y - q1[r], d2 = v.z - q2[r];
+              mp[r] = fmaxf(mp[r], lw - fmaf(d2, d2, fmaf(d1, d1, d0 * d0)));
+            }
+          }
+          float mm = INFINITY;
+#pragma unroll
+          for (int r = 0; r < FR; ++r) if (pk[r] >= 0) mm = fminf(mm, mp[r]);
+          mm = warp_min_f32(mm);
+          if (lane == 0) Mt[t] = (mm > -1.0e30f) ? mm : -INFINITY;
+        }
+        __syncthreads();
+      }
+      // Work items = (tile) x (slice of the sample blocks): the likelihood is linear in the pair sums, so a warp
+      // multiplies its PARTIAL sum of a point by the point's catalogue factor; slices make the item count a multiple of
+      // the warp count.  p_gw output wants complete sums per point: one slice then.
+      int S = 1;
+      while (!pout && (ntiles * S) % NW != 0 && S < 8 && nblk / (2 * S) >= 4) S *= 2;
+      const int bper = (nblk + S - 1) / S;
+      for (int it = warp; it < ntiles * S; it += NW) {
+        const int t = it / S, blo = (it - t * S) * bper, bhi = min(nblk, blo + bper);
+        float q0[FR], q1[FR], q2[FR], acc[FR], t2lo, t2hi;
+        int pk[FR];
+        tile_points(t, q0, q1, q2, pk, t2lo, t2hi);
+#pragma unroll
+        for (int r = 0; r < FR; ++r) acc[r] = 0.f;
+        const float Mtile = win3 ? Mt[t] : -INFINITY;
         // Two points per packed operand: the same d0^2 + d1^2 + d2^2 (same operation order and roundings as the scalar
         // form) in 6 packed instructions per two pairs instead of 12, so the loop is bound by MUFU.EX2, not by issue.
         f32x2 nq0[FR / 2], nq1[FR / 2], nq2[FR / 2], acc2[FR / 2];
@@ -740,17 +806,25 @@ numerator_f32_kernel(const NumArgs a) {
           nq0[r] = pk2(-q0[2 * r], -q0[2 * r + 1]); nq1[r] = pk2(-q1[2 * r], -q1[2 * r + 1]);
           nq2[r] = pk2(-q2[2 * r], -q2[2 * r + 1]); acc2[r] = 0ull;
         }
+        for (int b = blo; b < bhi; ++b) {
+          if (win3) {
+            const float4 hb = blkh[b];
+            const float dist = fmaxf(fmaxf(hb.x - t2hi, t2lo - hb.y), 0.f);
+            if (hb.z + 6.f - dist * dist < Mtile - a.win_t2) continue;      // (option kde_win_t2, default 24 bits: fp32 carries 24)
+          }
+          const int jlo = b * SB, jhi = min(Ns, jlo + SB);
 #pragma unroll 4
-        for (int j = jlo; j < jhi; ++j) {
-          const float4 v = yw[j];
-          const f32x2 vx = pk2(v.x, v.x), vy = pk2(v.y, v.y), vz = pk2(v.z, v.z), vw = pk2(v.w, v.w);
+          for (int j = jlo; j < jhi; ++j) {
+            const float4 v = yw[j];
+            const f32x2 vx = pk2(v.x, v.x), vy = pk2(v.y, v.y), vz = pk2(v.z, v.z), vw = pk2(v.w, v.w);
 #pragma unroll
-          for (int r = 0; r < FR / 2; ++r) {
-            const f32x2 d0 = add2(vx, nq0[r]), d1 = add2(vy, nq1[r]), d2 = add2(vz, nq2[r]);
-            const f32x2 e = fma2(d2, d2, fma2(d1, d1, mul2(d0, d0)));
-            float e0, e1;
-            upk2(e, e0, e1);
-            acc2[r] = fma2(vw, pk2(ex2_ftz(-e0), ex2_ftz(-e1)), acc2[r]);
+            for (int r = 0; r < FR / 2; ++r) {
+              const f32x2 d0 = add2(vx, nq0[r]), d1 = add2(vy, nq1[r]), d2 = add2(vz, nq2[r]);
+              const f32x2 e = fma2(d2, d2, fma2(d1, d1, mul2(d0, d0)));
+              float e0, e1;
+              upk2(e, e0, e1);
+              acc2[r] = fma2(vw, pk2(ex2_ftz(-e0), ex2_ftz(-e1)), acc2[r]);
+            }
           }
         }
 #pragma unroll

@@ -158,6 +158,34 @@ def test_c4_full_3d_kde_vs_oracle(cb):
       assert _err(lle[j], ref) < tol, (fp_mode, h0)
 
 
+def test_full_3d_windows_match_all_pairs(cb):
+  """'full' 3-D KDE, fp32 mode: the sample-block windows (blocks of dL-sorted samples far from a tile of evaluation points
+  in the z-only whitened coordinate are skipped when below 2^-30 of the largest term at every point of the tile) against
+  the same kernel visiting every pair (`kde_win=0`): per-event log-likelihoods, and the p_gw arrays INCLUDING their far
+  tails (relative agreement wherever the density is above 1e-30 of its maximum)."""
+  from chimera_b200 import synth
+  ev = synth.make_events(12, 4096, seed=71, sky=True)
+  zg = synth.make_z_grids(ev["dL"], z_int_res=200, H0_prior=(30., 140.))      # a wide grid: many points far from the samples
+  ev = synth.pixelize(ev, nside_list=(64, 32), mean_npixels_event=14)
+  p_cat, P_compl = synth.smooth_p_cat(ev, zg, seed=72)
+  th = cb.theta_pe_det(**{k: ev[k] for k in ("m1det", "m2det", "dL", "pe_prior", "ra", "dec", "opt_nsides",
+                                             "pixels_opt_nsides", "ra_pix", "dec_pix", "gw_loc2d_pdf",
+                                             "pixels_pe_opt_nside")})
+  gcat = cb.pixelated_catalog(cb.dVdz_completeness(np.array([0.073, 1.3])), p_cat=p_cat, P_compl=P_compl)
+  pop = cb.population(cb.cosmo.flrw(z_max=5.), cb.mass.plp(), cb.rate.madau_dickinson(), gal_cat=gcat)
+  H0 = np.array([45., 70., 110.])
+  out = {}
+  for name, opt in (("win", {}), ("all", {"kde_win": 0})):
+    like = cb.hyperlikelihood(th, zg, pop, None, kind_p_gw3d="full", kernel="gauss", fp_mode="fp32", options=opt)
+    out[name] = (like.compute_all(H0=H0)[0], like.p_gw3dfull(pop.update(H0=70.)))
+  assert _err(out["win"][0], out["all"][0]) < 2e-6
+  pw, pa = out["win"][1], out["all"][1]
+  big = pa > 1e-30 * np.max(pa)
+  assert big.sum() > 1000
+  np.testing.assert_allclose(pw[big], pa[big], rtol=2e-5)
+  assert np.all(pw[~big] <= 1e-29 * np.max(pa))
+
+
 def test_c5_modified_gravity_walker_batch(cb):
   """C5 shape at reduced event count: mg_flrw (Xi0, n) + mass + rate hyper-parameters, a 4096-point walker matrix
   through the sampler front end in ONE batched call; a strided subset against the oracle, the rest against
