@@ -23,6 +23,10 @@
 
 #define F_NT 256
 #define F_NW (F_NT / 32)
+#ifndef F_NT_FULL2
+#define F_NT_FULL2 512            // 'full', MODE 2 (one CTA per SM: 120 KB of staged samples): 16 warps instead of 8
+#endif
+static inline int f32_threads(int kind, int mode) { return (kind == CHB_PGW_FULL && mode == 2) ? F_NT_FULL2 : F_NT; }
 // tuning knobs of the split fast path (build.py passes -D overrides from CHB_BUILD_DEFS for A/B runs)
 #ifndef CHB_K1_MINB
 #define CHB_K1_MINB 3        // co-resident CTAs per SM the reweighting kernel (MODE 1) is compiled for
@@ -58,7 +62,7 @@ __host__ __device__ inline FPlan make_fplan(int tab_doubles, int Nz, int B, int 
   p.bs = o; o += B;
   p.xwb = o; o += B;
   p.part = o; o += (nw * Nz + 1) / 2;
-  p.red = o; o += 64;
+  p.red = o; o += (nw > 8) ? 128 : 64;      // block_stats: 6 doubles per warp
   o = (o + 1) & ~1;
   p.stage = o; o += (kind == CHB_PGW_FULL ? 3 : 1) * Ns;     // float2 {z,w} [+ float4 whitened]
   p.total = o;
@@ -67,7 +71,7 @@ __host__ __device__ inline FPlan make_fplan(int tab_doubles, int Nz, int B, int 
 static inline int f32_tab_doubles(const TableLayout& lay) { return lay.f32_core() - lay.f32_dl4(); }
 
 size_t numerator_f32_smem_bytes(const NumArgs& a, int mode) {
-  return (size_t)make_fplan(f32_tab_doubles(a.mc.lay), a.Nz, a.binning ? a.num_bins : 0, a.Ns, a.kind, mode, F_NW).total * sizeof(double);
+  return (size_t)make_fplan(f32_tab_doubles(a.mc.lay), a.Nz, a.binning ? a.num_bins : 0, a.Ns, a.kind, mode, f32_threads(a.kind, mode) / 32).total * sizeof(double);
 }
 
 __device__ __forceinline__ double nan_to_num_log_f(double like) {
@@ -874,7 +878,7 @@ static inline int kind_group(int kind) { return kind == CHB_PGW_MARG ? 1 : (kind
     case 5: { auto kern = numerator_f32_kernel<1, 2, F_NT>; EXPR; } break;                           \
     case 6: { auto kern = numerator_f32_kernel<2, 0, F_NT>; EXPR; } break;                           \
     case 7: { auto kern = numerator_f32_kernel<2, 1, F_NT>; EXPR; } break;                           \
-    default: { auto kern = numerator_f32_kernel<2, 2, F_NT>; EXPR; } break;                          \
+    default: { auto kern = numerator_f32_kernel<2, 2, F_NT_FULL2>; EXPR; } break;                          \
   }
 // `optin`: the device's opt-in maximum of shared memory per block; the attribute is set to that maximum minus the kernel's
 // static shared memory (the limit applies to static + dynamic), never to a handle's own footprint.
@@ -890,11 +894,11 @@ cudaError_t numerator_f32_configure(int kind, int mode, size_t optin) {
 int numerator_f32_ctas_per_sm(int kind, int mode, size_t smem) {
   int n = 0;
   cudaError_t e = cudaSuccess;
-  CHB_F32_DISPATCH(kind_group(kind), mode, e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, F_NT, smem));
+  CHB_F32_DISPATCH(kind_group(kind), mode, e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, f32_threads(kind, mode), smem));
   if (e != cudaSuccess) { cudaGetLastError(); return 0; }
   return n;
 }
 cudaError_t launch_numerator_f32(const NumArgs& a, int mode, int grid, size_t smem, cudaStream_t s) {
-  CHB_F32_DISPATCH(kind_group(a.kind), mode, (kern<<<grid, F_NT, smem, s>>>(a)));
+  CHB_F32_DISPATCH(kind_group(a.kind), mode, (kern<<<grid, f32_threads(a.kind, mode), smem, s>>>(a)));
   return cudaGetLastError();
 }
