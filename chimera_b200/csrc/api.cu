@@ -259,6 +259,42 @@ int chb_set_injections(chb_handle* h, int64_t Ninj, const double* m1det, const d
   if (Ninj < 1 || Ninj > 0x7fffffff || !m1det || !m2det || !dL || !p_draw)
     return fail(h, CHB_ERR_INVALID, "bad injection arrays");
   DevGuard _dg(h->cfg.device);
+  // The two sums over the injections do not depend on their order (selection_function.py:37-44), so the injections are
+  // stored sorted by an estimate of the source-frame secondary mass, m2det / (1 + z_fid(dL)) with z_fid from a fixed flat
+  // LCDM (H0 = 70, Om0 = 0.3): the 32 injections a warp evaluates together then lie on the same side of the low-mass
+  // taper m_low + delta_m, and the warps above it skip the taper's eight MUFU operations per injection (selection.cu).
+  std::vector<int> perm((size_t)Ninj);
+  {
+    const int NT = 4096;                                 // dL(z) of the fiducial cosmology on a log grid of z in [1e-4, 100]
+    std::vector<double> tz(NT), td(NT);
+    double dc = 0.0, zp = 0.0;
+    for (int i = 0; i < NT; ++i) {
+      const double z = std::pow(10.0, -4.0 + 6.0 * i / (NT - 1));
+      const int sub = 8;
+      for (int k = 0; k < sub; ++k) {                    // midpoint rule for int dz / E
+        const double zm = zp + (z - zp) * (k + 0.5) / sub;
+        dc += (z - zp) / sub / std::sqrt(0.3 * (1 + zm) * (1 + zm) * (1 + zm) + 0.7);
+      }
+      zp = z; tz[i] = z; td[i] = 4282.7494 * dc * (1.0 + z);
+    }
+    std::vector<float> key((size_t)Ninj);
+    for (int64_t i = 0; i < Ninj; ++i) {
+      const double d = dL[i];
+      double z;
+      if (!(d > td[0])) z = (d > 0.0) ? d / 4282.7494 : 0.0;
+      else if (d >= td[NT - 1]) z = tz[NT - 1];
+      else {
+        const int k = (int)(std::upper_bound(td.begin(), td.end(), d) - td.begin());
+        z = tz[k - 1] + (tz[k] - tz[k - 1]) * (d - td[k - 1]) / (td[k] - td[k - 1]);
+      }
+      key[i] = (float)(m2det[i] / (1.0 + z));
+      perm[i] = (int)i;
+    }
+    std::sort(perm.begin(), perm.end(), [&key](int x, int y) { return key[x] < key[y] || (key[x] == key[y] && x < y); });
+  }
+  std::vector<double> t1((size_t)Ninj), t2((size_t)Ninj), t3((size_t)Ninj), t4((size_t)Ninj);
+  for (int64_t i = 0; i < Ninj; ++i) { const int q = perm[i]; t1[i] = m1det[q]; t2[i] = m2det[q]; t3[i] = dL[q]; t4[i] = p_draw[q]; }
+  m1det = t1.data(); m2det = t2.data(); dL = t3.data(); p_draw = t4.data();
   CU(h->inj_m1.upload(m1det, Ninj), "upload inj m1det");
   CU(h->inj_m2.upload(m2det, Ninj), "upload inj m2det");
   CU(h->inj_dL.upload(dL, Ninj), "upload inj dL");

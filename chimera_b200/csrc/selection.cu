@@ -106,15 +106,20 @@ selection_f32_kernel(SelArgs a) {
   const long long j1 = min((long long)a.Ninj, j0 + chunk);
   double s1 = 0.0, s2 = 0.0;
   // software pipeline: the packed injection of the next iteration is requested before the current one is
-  // evaluated (the loads are L2 hits ~600 cycles away; the arithmetic of one injection is ~200 instructions)
+  // evaluated (the loads are L2 hits ~600 cycles away; the arithmetic of one injection is ~200 instructions).
+  // Every thread runs the same number of iterations (tail lanes re-evaluate the tile's last injection with weight 0), so
+  // the warp can vote: the injections are stored sorted by their (estimated) source-frame secondary mass (api.cu), and a
+  // warp whose 32 injections are all above m_low + delta_m skips the taper.
+  const int iters = (int)((j1 - j0 + blockDim.x - 1) / blockDim.x);
+  const long long jlast = (j1 > j0) ? j1 - 1 : j0;
   long long j = j0 + tid;
   float4 sv = make_float4(1.f, 1.f, 1.f, 0.f);
   float2 lv = make_float2(0.f, 0.f);
-  if (j < j1) { sv = __ldg(a.s4 + j); lv = __ldg(a.l2 + j); }
-  while (j < j1) {
+  if (iters > 0) { sv = __ldg(a.s4 + min(j, jlast)); lv = __ldg(a.l2 + min(j, jlast)); }
+  for (int it = 0; it < iters; ++it) {
     const long long jn = j + blockDim.x;
     float4 nsv = sv; float2 nlv = lv;
-    if (jn < j1) { nsv = __ldg(a.s4 + jn); nlv = __ldg(a.l2 + jn); }
+    if (it + 1 < iters) { nsv = __ldg(a.s4 + min(jn, jlast)); nlv = __ldg(a.l2 + min(jn, jlast)); }
     // z_from_dGW without the zi4 clamp row: same scan, clamp with the staged last knot
     int b = (int)(__float_as_uint(sv.x) >> CHB_LUT_SHIFT) - (int)fc.b0;
     b = max(0, min(b, fc.nb - 1));
@@ -126,8 +131,12 @@ selection_f32_kernel(SelArgs a) {
     if (sv.x <= 0.f) z = 0.f;
     const float opz = 1.f + z;
     const float r = rcpf_(opz), lz = lg2f_(opz);
-    const float pm = weight_f32(fc, sv.y * r, sv.z * r, lv.x - lz, lv.y - lz, sv.w);   // p_m1m2 / p_draw
-    const float wf = cr.R0 * pm * zterm_inj_f32(cr, z, opz, lz, sv.x);
+    const float m1 = sv.y * r, m2 = sv.z * r;
+    // (m2 <= m1 inside the support, so the taper test on m2 covers m1 whenever the weight is not already zero)
+    const bool taper = !(m2 - fc.lo > fc.dm);
+    const float pm = __any_sync(0xffffffffu, taper) ? weight_bf<true>(fc, m1, m2, lv.x - lz, lv.y - lz, sv.w)
+                                                    : weight_bf<false>(fc, m1, m2, lv.x - lz, lv.y - lz, sv.w);   // p_m1m2 / p_draw
+    const float wf = (j < j1) ? cr.R0 * pm * zterm_inj_f32(cr, z, opz, lz, sv.x) : 0.f;
     const double w = (double)wf;
     if (wf == wf) s1 += w;
     s2 += w * w;
