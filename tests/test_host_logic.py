@@ -231,3 +231,19 @@ def test_builtin_ensemble_sampler_recovers_a_gaussian():
   assert np.all((tg[:, 0] >= 69.) & (tg[:, 0] <= 71.))
   with pytest.raises(ValueError):
     sampling.EnsembleSampler(5, 3, log_prob)
+
+
+def test_bench_arms_share_one_config_object():
+  """bench.py: the `config` object of the JSON line is built by ONE function for both arms (`--impl ours` and
+  `--impl reference`), for every N the driver launches -- it names the workload, not the implementation."""
+  import argparse
+  import bench
+  for gpus in (1, 2, 8):
+    a = argparse.Namespace(config="C3", scaling="strong", nev=0, ninj=0, hyper_groups=1, fp_mode="fp32", options="")
+    c = bench.line_config(a, gpus)
+    assert c["events_total"] == 1000 and c["n_hyper"] == 256 and c["samples_per_event"] == 5000
+    assert c["events_per_gpu"] == 1000 // gpus and c["injections_total"] == 1_000_000
+    assert "workload" in c and "l2" in c and not any(k in c for k in ("model", "global_batch", "seq_len"))
+    assert c == bench.line_config(a, gpus)
+  w = bench.line_config(argparse.Namespace(config="C3", scaling="weak", nev=0, ninj=0, hyper_groups=1, fp_mode="fp32", options=""), 4)
+  assert w["events_total"] == 4000 and w["events_per_gpu"] == 1000
