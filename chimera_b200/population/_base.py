@@ -34,7 +34,17 @@ class base_struct:
     return f"{self.__class__.__name__}({', '.join(f'{k}={getattr(self, k)!r}' for k in self.keys)})"
 
   def _is_scalar(self):
-    return all(np.ndim(getattr(self, k)) == 0 for k in self.keys)
+    return all(_ndim(getattr(self, k)) == 0 for k in self.keys)
+
+
+def _ndim(v):
+  """np.ndim without its dispatch overhead for the two common cases (this runs ~40 times per likelihood call)."""
+  nd = getattr(v, "ndim", None)
+  if nd is not None:
+    return nd
+  if isinstance(v, (int, float)):
+    return 0
+  return np.ndim(v)
 
 
 def fill_rows(rows, struct):
@@ -42,7 +52,7 @@ def fill_rows(rows, struct):
   for k in struct.keys:
     slot = _lib.SLOT.get(k)
     if slot is not None:
-      rows[:, slot] = np.asarray(getattr(struct, k), dtype=np.float64)
+      rows[:, slot] = getattr(struct, k)
 
 
 def batch_size(*structs_and_scalars):
@@ -50,41 +60,36 @@ def batch_size(*structs_and_scalars):
   for s in structs_and_scalars:
     vals = [getattr(s, k) for k in s.keys] if isinstance(s, base_struct) else [s]
     for v in vals:
-      if np.ndim(v) == 1:
+      nd = _ndim(v)
+      if nd == 1:
         if n is not None and n != len(v):
           raise ValueError("batched hyper-parameters must have equal lengths")
         n = len(v)
-      elif np.ndim(v) > 1:
+      elif nd > 1:
         raise ValueError("hyper-parameters must be scalars or 1-D arrays")
   return n
 
 
+_NEUTRAL = dict(H0=70., Om0=0.25, w0=-1., Xi0=1., z_max=10., m_low=5.1, m_high=87., alpha=3.4, beta=1.1, delta_m=4.8,
+                alpha_2=5.6, break_fraction=0.43, lambda_peak=0.039, mu_g=34., sigma_g=3.6, gamma=2.7, kappa=3., zp=2.,
+                zmax=1.3)
+_template = None
+
+
 def base_rows(n, cosmo=None, mass=None, rate=None, R0=1.0):
-  rows = np.zeros((n, _lib.CHB_NPAR))
-  # neutral values for slots a model does not own
-  rows[:, _lib.SLOT["H0"]] = 70.
-  rows[:, _lib.SLOT["Om0"]] = 0.25
-  rows[:, _lib.SLOT["w0"]] = -1.
-  rows[:, _lib.SLOT["Xi0"]] = 1.
-  rows[:, _lib.SLOT["z_max"]] = 10.
-  rows[:, _lib.SLOT["m_low"]] = 5.1
-  rows[:, _lib.SLOT["m_high"]] = 87.
-  rows[:, _lib.SLOT["alpha"]] = 3.4
-  rows[:, _lib.SLOT["beta"]] = 1.1
-  rows[:, _lib.SLOT["delta_m"]] = 4.8
-  rows[:, _lib.SLOT["alpha_2"]] = 5.6
-  rows[:, _lib.SLOT["break_fraction"]] = 0.43
-  rows[:, _lib.SLOT["lambda_peak"]] = 0.039
-  rows[:, _lib.SLOT["mu_g"]] = 34.
-  rows[:, _lib.SLOT["sigma_g"]] = 3.6
-  rows[:, _lib.SLOT["gamma"]] = 2.7
-  rows[:, _lib.SLOT["kappa"]] = 3.
-  rows[:, _lib.SLOT["zp"]] = 2.
-  rows[:, _lib.SLOT["zmax"]] = 1.3
+  global _template
+  if _template is None:
+    # neutral values for slots a model does not own
+    t = np.zeros(_lib.CHB_NPAR)
+    for k, v in _NEUTRAL.items():
+      t[_lib.SLOT[k]] = v
+    _template = t
+  rows = np.empty((n, _lib.CHB_NPAR))
+  rows[:] = _template
   for s in (cosmo, mass, rate):
     if s is not None:
       fill_rows(rows, s)
-  rows[:, _lib.SLOT["R0"]] = np.asarray(R0, dtype=np.float64)
+  rows[:, _lib.SLOT["R0"]] = R0
   # end knots of m_grid exactly as jnp.logspace(log10 m_low, log10 m_high, res) yields them
   # (mass.py:46): whether they pass `m_low <= m <= m_high` depends on the last ulp.
   rows[:, 26] = np.power(10., np.log10(rows[:, _lib.SLOT["m_low"]]))
