@@ -612,6 +612,10 @@ static __device__ __noinline__ void fu_kde_win(const float4* __restrict__ stage,
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   WinPlan wp; wp.R = R; wp.LPS = LPS; wp.chunk = chunk; wp.nchunks = nchunks;
   const float h = (float)hd;
+  // the per-warp rows phase C adds to: zeroed HERE, in front of the barrier below -- not by the caller, whose other KDE
+  // routines (fu_direct, fu_epan_blocks) write this region without a barrier of their own in front (compute-sanitizer
+  // racecheck found exactly that write-after-write hazard when the zeroing stood right after the reweighting)
+  for (int i = tid; i < FU_NW * G; i += FU_NT) rows[i] = 0.0;
   if (tid < 16) cr[tid] = exp2f(-(h * h) * (float)(tid * (tid - 1)));
   if (warp == 1 && lane < nchunks) {
     float lo = INFINITY, hi = -INFINITY, lm = -INFINITY, xm = 0.f;
@@ -684,7 +688,6 @@ numerator_fused_kernel(const NumArgs a) {
       }
     }
     __syncthreads();                                         // publishes stage[], sub[] and the warp partials
-    for (int i = tid; i < FU_NW * G; i += FU_NT) rows[i] = 0.0;     // (every KDE routine has a barrier before it adds to them)
 #if CHB_FU_TAILPF
     if ((tid & 15) == 0) {
       // one hint per 128-byte line (16 doubles / float2) of the rows of the z-integral
