@@ -288,6 +288,7 @@ int chb_set_injections(chb_handle* h, int64_t Ninj, const double* m1det, const d
         z = tz[k - 1] + (tz[k] - tz[k - 1]) * (d - td[k - 1]) / (td[k] - td[k - 1]);
       }
       key[i] = (float)(m2det[i] / (1.0 + z));
+      if (!(key[i] == key[i])) key[i] = INFINITY;          // NaN input: last, and the comparator stays a strict weak order
       perm[i] = (int)i;
     }
     std::sort(perm.begin(), perm.end(), [&key](int x, int y) { return key[x] < key[y] || (key[x] == key[y] && x < y); });
@@ -367,7 +368,11 @@ static int prepare(chb_handle* h) {
       const size_t o = (size_t)e * Ns;
       for (int64_t j = 0; j < Ns; ++j) perm[j] = (int)j;
       const double* key = p3 + o;
-      std::sort(perm.begin(), perm.end(), [key](int x, int y) { return key[x] < key[y] || (key[x] == key[y] && x < y); });
+      // (NaN distances sort last: the comparator must stay a strict weak order whatever the input holds)
+      std::sort(perm.begin(), perm.end(), [key](int x, int y) {
+        const double a = (key[x] == key[x]) ? key[x] : INFINITY, b = (key[y] == key[y]) ? key[y] : INFINITY;
+        return a < b || (a == b && x < y);
+      });
       for (int64_t j = 0; j < Ns; ++j) {
         const size_t d = o + j, s = o + perm[j];
         t1[d] = p1[s]; t2[d] = p2[s]; t3[d] = p3[s]; t4[d] = p4[s];
