@@ -121,3 +121,27 @@ def test_window_model_all_tilings(mult):
       # (fp32 rounding of d^2 at d ~ 20 scaled units: 2 d ulp(d) ln 2 ~ 1e-4)
       assert (np.abs(dens[outside] - exact[outside]) / exact[outside]).max() < 5e-4
   assert seen
+
+
+@pytest.mark.parametrize("n", [1000, 700, 512, 449])
+@pytest.mark.parametrize("kind", ["bulk", "heavy_tail", "sparse"])
+def test_window_model_short_events(n, kind):
+  """Events with few samples (walker batches with ~1000 samples per event): the plan halves the loop iterations per pass
+  (32 -> 16 -> 8) until there are at least 8 chunks instead of refusing windows; the same guarantees hold with the
+  short chunks.  Below 449 samples (8 chunks of 64) the plan still refuses and the kernel sums directly."""
+  from window_model import plan
+  rng = np.random.default_rng(n + len(kind))
+  z, w = _case(rng, kind, n=n)
+  out = _run(z, w, max(z.min() - 2 * z.std(), 1e-8), z.max() + 2 * z.std())
+  if out is None:
+    pytest.skip("the plan refuses windows for this bandwidth (window ~ whole grid)")
+  dens, info, lt, exact, g = out
+  assert info["nchunks"] >= 8 and info["chunk"] <= 128
+  big = lt >= (lt.max(axis=1, keepdims=True) - 30.0)
+  for gi, j in zip(*np.nonzero(big)):
+    ia, ib = info["win"][j // info["chunk"]]
+    assert ia <= gi <= ib
+  assert np.abs(dens - exact).max() < 2e-6 * exact.max()
+  core = exact > 1e-8 * exact.max()
+  assert (np.abs(dens[core] - exact[core]) / exact[core]).max() < 3e-5
+  assert plan(150, 300, 0.3) is None                   # 300 samples: no window plan
